@@ -1,0 +1,19 @@
+# Builds libmacb200.so (sm_100a only) in-tree.  `python -c "import __graft_entry__ as g; g.build()"` runs this.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr
+SRC := mac_b200/csrc/api.cu mac_b200/csrc/tridiag.cpp
+HDR := mac_b200/csrc/kernels.cuh mac_b200/csrc/tridiag.h include/macb200.h
+OUT := mac_b200/libmacb200.so
+
+all: $(OUT)
+
+$(OUT): $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC)
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/macb_ptxas.so $(SRC) 2>&1 | grep -E 'Compiling|registers|spill' 
+
+clean:
+	rm -f $(OUT)
+.PHONY: all clean ptxas-info

@@ -1,0 +1,153 @@
+/* macb200.h -- C-ABI of libmacb200.so: the B200 (sm_100a) Frank-Wolfe / Fiedler hot path of MAC.
+ *
+ * The reference (MarineRoboticsGroup/mac) is pure Python and has no FFI layer; its boundary for
+ * this path is the Python call surface of `mac.solvers.mac.MAC` and `mac.optimization.frankwolfe`.
+ * Each entry point below names the reference site it replaces (paths relative to the reference
+ * root; `nx:` = networkx/linalg/algebraicconnectivity.py, the third-party module fiedler.py:42
+ * calls).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer argument is HOST memory owned by the caller;
+ *   - every call returns an int status (MACB_OK = 0); `macb_last_error` gives the message;
+ *   - a handle owns all device memory, one CUDA stream and its CUDA-graph cache; it is bound to
+ *     one device and is NOT thread-safe (one handle per thread / GPU);
+ *   - calls are synchronous: results are in the caller's buffers when the call returns;
+ *   - all floating point is IEEE double; indices are int32; counts are int64.
+ */
+#ifndef MACB200_H
+#define MACB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct macb_ctx* macb_handle;
+
+enum {
+    MACB_OK = 0,
+    MACB_NOT_CONVERGED = 1,   /* eigen-iteration hit max_steps; outputs hold the best estimate   */
+    MACB_ERR_ARG = -1,        /* bad argument (the reference raises AssertionError)              */
+    MACB_ERR_CUDA = -2,       /* CUDA runtime error; message has the cudaError string            */
+    MACB_ERR_STATE = -3,      /* call order violated (e.g. gradient before fiedler)              */
+    MACB_ERR_NOMEM = -4
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Replaces MAC.__init__ (mac/solvers/mac.py:22-72): uploads the fixed and candidate edge lists,
+ * builds the fixed union sparsity pattern of L(w) = L_fixed + sum_k w_k kappa_k L_k once (CSR,
+ * off-diagonals only; the diagonal is the weighted degree), and the slot -> edge map the assembly
+ * kernel uses.  Self loops contribute nothing (graphs.py:77-96 nets them to zero) and are skipped.
+ * The feasibility asserts of mac.py:46-52 are checked by the Python mirror, not here.
+ * `device` < 0 keeps the current device. */
+int macb_create(int32_t n,
+                int64_t nf, const int32_t* fi, const int32_t* fj, const double* fw,
+                int64_t m, const int32_t* ci, const int32_t* cj, const double* ckappa,
+                int device, macb_handle* out);
+int macb_destroy(macb_handle h);
+
+/* Message for the last non-OK status on `h`; with h == NULL, the last macb_create failure. */
+const char* macb_last_error(macb_handle h);
+
+/* ---- Laplacian L(x) -------------------------------------------------------------------------- */
+
+/* Replaces MAC.laplacian (mac.py:74-89) + weight_graph_lap_from_edges (graphs.py:58-98):
+ * uploads x[m] and rewrites the CSR values of L(x) in place on the device; candidate k
+ * contributes x_k kappa_k iff x_k > min_sel_tol (mac.py:85). */
+int macb_set_x(macb_handle h, const double* x, double min_sel_tol);
+int macb_get_x(macb_handle h, double* x);
+
+/* y = L(x) v for host vectors of length n (replaces the scipy `L @ X` at nx:237); test / roofline. */
+int macb_spmv(macb_handle h, const double* v, double* y);
+
+/* max_i sum_j |L_ij| of the current L(x) (nx:229). */
+int macb_lnorm(macb_handle h, double* lnorm);
+
+/* ---- Fiedler pair ---------------------------------------------------------------------------- */
+
+/* Start vector of the eigen-iteration (fiedler.py:27-32 seeds a fresh RandomState(7) block per
+ * call; the Python mirror passes that block's first column).  NULL selects the built-in
+ * deterministic generator.  The vector is copied. */
+int macb_set_start(macb_handle h, const double* x0);
+
+/* Replaces find_fiedler_pair (fiedler.py:9-44) -> networkx _tracemin_fiedler (nx:149-253) on the
+ * current L(x).  Deflated Lanczos on the complement of the all-ones vector; stops when the TRUE
+ * residual meets the reference's test ||L v - lambda v||_1 / ||L||_inf < tol (nx:243-245).
+ * v has unit 2-norm and zero mean.  warm != 0 starts from the previous Fiedler vector.
+ * Any output pointer may be NULL. */
+int macb_fiedler(macb_handle h, double tol, int max_steps, int warm,
+                 double* lambda2, double* v, int* steps, double* resid);
+
+/* ---- gradient / LP step ---------------------------------------------------------------------- */
+
+/* Replaces the gradient loop of MAC.problem (mac.py:117-124): g_k = kappa_k (v_i - v_j)^2 from the
+ * Fiedler vector of the last macb_fiedler call.  g may be NULL (device-only). */
+int macb_gradient(macb_handle h, double* g);
+
+/* Replaces solve_subset_box_lp(g, k) (constraints.py:12-22 -> rounding.py:21-28) on the device
+ * gradient: s[m] in {0,1} marks the k largest entries; ties at the k-th value go to the lowest
+ * index.  s may be NULL. */
+int macb_topk(macb_handle h, int64_t k, double* s);
+
+/* Same LP oracle for an arbitrary host vector g[m] (no handle state involved). */
+int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s);
+
+/* ---- whole Frank-Wolfe loop ------------------------------------------------------------------- */
+
+/* Replaces frank_wolfe (frankwolfe.py:10-79) specialised as MAC.solve calls it (mac.py:186-200):
+ * problem = MAC.problem, solve_lp = top-k, step 2/(i+2), dual bound u = min(u, f + g.(s - x)),
+ * stop tests ||g||_2 < grad_norm_tol and (u - f) < rel_gap_tol |f|.  x_init[m] in, w[m] out.
+ * f_hist / u_hist (length >= max_iters, may be NULL) receive f and u per iteration. */
+int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters,
+                double rel_gap_tol, double grad_norm_tol, double fiedler_tol, double min_sel_tol,
+                int fiedler_max_steps, int warm,
+                double* w, double* u, int* iters_done, double* f_hist, double* u_hist);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+
+enum {
+    MACB_T_ASSEMBLE = 0, MACB_T_FIEDLER, MACB_T_GRADIENT, MACB_T_TOPK, MACB_T_UPDATE, MACB_T_COPY,
+    MACB_T_COUNT
+};
+/* Cumulative counters since the last reset: kernels launched (graph nodes counted individually),
+ * SpMV launches, Lanczos steps, Fiedler solves, and -- when profiling is on -- CUDA-event
+ * milliseconds per phase (MACB_T_*).  Any pointer may be NULL. */
+int macb_counters(macb_handle h, int64_t* kernel_launches, int64_t* spmv_launches,
+                  int64_t* lanczos_steps, int64_t* fiedler_solves, double* phase_ms /*[MACB_T_COUNT]*/);
+int macb_reset_counters(macb_handle h);
+int macb_set_profile(macb_handle h, int on);
+
+/* `reps` back-to-back launches of the SpMV kernel on the current L(x), timed with CUDA events on
+ * the handle's stream; flush_l2 != 0 rewrites a > L2-sized buffer before every launch (each
+ * launch then timed on its own).  Returns the average milliseconds per launch and the
+ * algorithmic bytes of one launch. */
+int macb_spmv_bench(macb_handle h, int reps, int flush_l2, double* avg_ms, double* algo_bytes);
+
+/* Sizes of the device-resident problem: n, m, off-diagonal slots of the union pattern, and the
+ * slots active (non-zero) in the current L(x). */
+int macb_sizes(macb_handle h, int64_t* n, int64_t* m, int64_t* nnz_union, int64_t* nnz_active);
+
+/* Writes a buffer larger than L2 (bench hygiene between timed steps). */
+int macb_l2_flush(macb_handle h);
+
+/* ---- host-only helpers (no GPU needed; exported for the CPU test-suite) ----------------------- */
+
+/* Smallest eigenpair of the symmetric tridiagonal T_k (diagonal a[0..k), off-diagonal b[1..k)):
+ * bisection on the Sturm count + twisted factorisation.  This is the Rayleigh-Ritz step the
+ * Lanczos driver runs on the host (the reference's counterpart is the 4x4 `eigh` at nx:239). */
+int macb_tridiag_smallest(const double* a, const double* b, int k, double* theta, double* s);
+
+/* Union-pattern CSR builder used by macb_create, host arrays out (row_ptr[n+1], col[nnz],
+ * eid[nnz]; nnz = 2 * (#non-loop edges)); edge ids: fixed e -> e, candidate k -> nf + k. */
+int macb_host_build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj,
+                            int64_t m, const int32_t* ci, const int32_t* cj,
+                            int32_t* row_ptr, int32_t* col, int32_t* eid, int64_t* nnz);
+
+const char* macb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACB200_H */

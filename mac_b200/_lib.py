@@ -1,0 +1,263 @@
+"""ctypes binding of libmacb200.so (include/macb200.h).  Thin by design: numpy arrays in, numpy out.
+
+There is NO fallback: if the shared library is missing, or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmacb200.so")
+
+MACB_OK = 0
+MACB_NOT_CONVERGED = 1
+T_NAMES = ["assemble", "fiedler", "gradient", "topk", "update", "copy"]
+
+
+class MacbError(RuntimeError):
+    """A libmacb200 call returned a negative status."""
+
+
+class MacbNotConverged(RuntimeWarning):
+    pass
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def _sig(fn, argtypes, restype=C.c_int):
+    fn.argtypes = argtypes
+    fn.restype = restype
+
+
+def lib():
+    """Load the library once.  Raises ImportError with the build hint when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "mac_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    _sig(L.macb_create, [C.c_int32, C.c_int64, _ip, _ip, _dp, C.c_int64, _ip, _ip, _dp, C.c_int, C.POINTER(H)])
+    _sig(L.macb_destroy, [H])
+    _sig(L.macb_last_error, [H], C.c_char_p)
+    _sig(L.macb_set_x, [H, _dp, C.c_double])
+    _sig(L.macb_get_x, [H, _dp])
+    _sig(L.macb_spmv, [H, _dp, _dp])
+    _sig(L.macb_lnorm, [H, _dp])
+    _sig(L.macb_set_start, [H, _dp])
+    _sig(L.macb_fiedler, [H, C.c_double, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int), _dp])
+    _sig(L.macb_gradient, [H, _dp])
+    _sig(L.macb_topk, [H, C.c_int64, _dp])
+    _sig(L.macb_topk_dense, [C.c_int, _dp, C.c_int64, C.c_int64, _dp])
+    _sig(L.macb_fw_run, [H, C.c_int64, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                         _dp, _dp, C.POINTER(C.c_int), _dp, _dp])
+    _sig(L.macb_counters, [H, _lp, _lp, _lp, _lp, _dp])
+    _sig(L.macb_reset_counters, [H])
+    _sig(L.macb_set_profile, [H, C.c_int])
+    _sig(L.macb_spmv_bench, [H, C.c_int, C.c_int, _dp, _dp])
+    _sig(L.macb_sizes, [H, _lp, _lp, _lp, _lp])
+    _sig(L.macb_l2_flush, [H])
+    _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
+    _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
+    _sig(L.macb_version, [], C.c_char_p)
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ) if a is not None and a.size else None
+
+
+class Handle:
+    """One graph resident on one GPU (macb_handle).  Not thread-safe."""
+
+    def __init__(self, n, fi, fj, fw, ci, cj, ckappa, device=-1):
+        L = lib()
+        self._L = L
+        self._h = C.c_void_p()
+        fi, fj, fw = _i32(fi), _i32(fj), _f64(fw)
+        ci, cj, ck = _i32(ci), _i32(cj), _f64(ckappa)
+        assert len(fi) == len(fj) == len(fw) and len(ci) == len(cj) == len(ck)
+        self.n, self.nf, self.m = int(n), len(fi), len(ci)
+        rc = L.macb_create(self.n, self.nf, _p(fi, _ip), _p(fj, _ip), _p(fw, _dp), self.m, _p(ci, _ip), _p(cj, _ip),
+                           _p(ck, _dp), int(device), C.byref(self._h))
+        if rc != MACB_OK:
+            raise MacbError(f"macb_create failed ({rc}): {L.macb_last_error(None).decode()}")
+
+    # -- plumbing
+    def _check(self, rc, what):
+        if rc == MACB_OK:
+            return
+        msg = self._L.macb_last_error(self._h).decode()
+        if rc == MACB_NOT_CONVERGED:
+            warnings.warn(f"{what}: {msg}", MacbNotConverged, stacklevel=3)
+            return
+        raise MacbError(f"{what} failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.macb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Laplacian
+    def set_x(self, x, min_sel_tol=1e-10):
+        x = _f64(x)
+        assert x.shape == (self.m,)
+        self._check(self._L.macb_set_x(self._h, _p(x, _dp), float(min_sel_tol)), "macb_set_x")
+
+    def get_x(self):
+        x = np.empty(self.m)
+        self._check(self._L.macb_get_x(self._h, _p(x, _dp)), "macb_get_x")
+        return x
+
+    def spmv(self, v):
+        v = _f64(v)
+        assert v.shape == (self.n,)
+        y = np.empty(self.n)
+        self._check(self._L.macb_spmv(self._h, _p(v, _dp), _p(y, _dp)), "macb_spmv")
+        return y
+
+    def lnorm(self):
+        out = C.c_double()
+        self._check(self._L.macb_lnorm(self._h, C.byref(out)), "macb_lnorm")
+        return out.value
+
+    # -- eigen-solve
+    def set_start(self, x0):
+        if x0 is None:
+            self._check(self._L.macb_set_start(self._h, None), "macb_set_start")
+            return
+        x0 = _f64(x0)
+        assert x0.shape == (self.n,)
+        self._check(self._L.macb_set_start(self._h, _p(x0, _dp)), "macb_set_start")
+
+    def fiedler(self, tol=1e-8, max_steps=0, warm=False, want_vector=True):
+        lam, res, steps = C.c_double(), C.c_double(), C.c_int()
+        v = np.empty(self.n) if want_vector else None
+        rc = self._L.macb_fiedler(self._h, float(tol), int(max_steps), int(bool(warm)), C.byref(lam),
+                                  _p(v, _dp) if want_vector else None, C.byref(steps), C.byref(res))
+        self._check(rc, "macb_fiedler")
+        return lam.value, v, {"steps": steps.value, "resid": res.value, "converged": rc == MACB_OK}
+
+    # -- gradient / LP
+    def gradient(self, want=True):
+        g = np.empty(self.m) if want else None
+        self._check(self._L.macb_gradient(self._h, _p(g, _dp) if want else None), "macb_gradient")
+        return g
+
+    def topk(self, k, want=True):
+        s = np.empty(self.m) if want else None
+        self._check(self._L.macb_topk(self._h, int(k), _p(s, _dp) if want else None), "macb_topk")
+        return s
+
+    # -- whole loop
+    def fw_run(self, k, x_init, max_iters, rel_gap_tol, grad_norm_tol, fiedler_tol=1e-8, min_sel_tol=1e-10,
+               fiedler_max_steps=0, warm=False):
+        x_init = _f64(x_init)
+        assert x_init.shape == (self.m,)
+        w = np.empty(self.m)
+        u = C.c_double()
+        iters = C.c_int()
+        fh = np.full(max(1, max_iters), np.nan)
+        uh = np.full(max(1, max_iters), np.nan)
+        rc = self._L.macb_fw_run(self._h, int(k), _p(x_init, _dp), int(max_iters), float(rel_gap_tol), float(grad_norm_tol),
+                                 float(fiedler_tol), float(min_sel_tol), int(fiedler_max_steps), int(bool(warm)),
+                                 _p(w, _dp), C.byref(u), C.byref(iters), _p(fh, _dp), _p(uh, _dp))
+        self._check(rc, "macb_fw_run")
+        it = iters.value
+        return w, u.value, {"iters": it, "f_hist": fh[:it].copy(), "u_hist": uh[:it].copy()}
+
+    # -- measurement
+    def counters(self):
+        a, b, c_, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        ms = (C.c_double * len(T_NAMES))()
+        self._L.macb_counters(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d), ms)
+        return {"kernel_launches": a.value, "spmv_launches": b.value, "lanczos_steps": c_.value,
+                "fiedler_solves": d.value, "phase_ms": dict(zip(T_NAMES, list(ms)))}
+
+    def reset_counters(self):
+        self._L.macb_reset_counters(self._h)
+
+    def set_profile(self, on):
+        self._L.macb_set_profile(self._h, int(bool(on)))
+
+    def spmv_bench(self, reps=200, flush_l2=False):
+        ms, by = C.c_double(), C.c_double()
+        self._check(self._L.macb_spmv_bench(self._h, int(reps), int(bool(flush_l2)), C.byref(ms), C.byref(by)),
+                    "macb_spmv_bench")
+        return ms.value, by.value
+
+    def sizes(self):
+        a, b, c_, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._L.macb_sizes(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d))
+        return {"n": a.value, "m": b.value, "nnz_union": c_.value, "nnz_active": d.value}
+
+    def l2_flush(self):
+        self._check(self._L.macb_l2_flush(self._h), "macb_l2_flush")
+
+
+def topk_dense(g, k, device=-1):
+    """solve_subset_box_lp on the device for an arbitrary host vector."""
+    L = lib()
+    g = _f64(g)
+    s = np.empty_like(g)
+    rc = L.macb_topk_dense(int(device), _p(g, _dp), g.size, int(k), _p(s, _dp))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_topk_dense failed ({rc}): {L.macb_last_error(None).decode()}")
+    return s
+
+
+def tridiag_smallest(a, b):
+    """Host helper (no GPU): smallest eigenpair of tridiag(a; b[1:])."""
+    L = lib()
+    a, b = _f64(a), _f64(b)
+    k = a.size
+    assert b.size >= k
+    th = C.c_double()
+    s = np.empty(k)
+    rc = L.macb_tridiag_smallest(_p(a, _dp), _p(b, _dp), k, C.byref(th), _p(s, _dp))
+    if rc != MACB_OK:
+        raise MacbError("macb_tridiag_smallest failed")
+    return th.value, s
+
+
+def host_build_pattern(n, fi, fj, ci, cj):
+    """Host helper (no GPU): the union CSR pattern macb_create builds."""
+    L = lib()
+    fi, fj, ci, cj = _i32(fi), _i32(fj), _i32(ci), _i32(cj)
+    cap = 2 * (len(fi) + len(ci))
+    rp = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(max(cap, 1), dtype=np.int32)
+    eid = np.empty(max(cap, 1), dtype=np.int32)
+    nnz = C.c_int64()
+    rc = L.macb_host_build_pattern(n, len(fi), _p(fi, _ip), _p(fj, _ip), len(ci), _p(ci, _ip), _p(cj, _ip),
+                                   _p(rp, _ip), _p(col, _ip), _p(eid, _ip), C.byref(nnz))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_host_build_pattern failed ({rc}): {L.macb_last_error(None).decode()}")
+    return rp, col[:nnz.value], eid[:nnz.value]

@@ -1,0 +1,941 @@
+// libmacb200.so -- C-ABI (include/macb200.h) and host-side drivers over the kernels in kernels.cuh.
+//
+// One handle = one graph (fixed + candidate edges) resident on one B200, one stream, one set of
+// captured CUDA graphs.  The Frank-Wolfe loop (frankwolfe.py:10-79 as called from mac.py:196) runs
+// entirely on the device; the host only (a) solves the tiny tridiagonal Rayleigh-Ritz problem of the
+// Lanczos iteration and (b) evaluates the two scalar stopping tests per FW iteration.
+#include "../../include/macb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tridiag.h"
+
+using namespace macb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kGraphSteps = 32;            // Lanczos steps per captured CUDA graph
+constexpr size_t kFlushBytes = 512u << 20; // > 126 MB L2
+
+struct CudaFail {
+    cudaError_t e;
+    const char* what;
+    int line;
+};
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__}; \
+    } while (0)
+
+struct ArgFail {
+    std::string msg;
+    int code;
+};
+
+template <typename T>
+T* dalloc(size_t count) {
+    T* p = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    return p;
+}
+
+}  // namespace
+
+struct macb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int grid_max = 148 * 8;
+    int W = 8;  // lanes per row in the row-parallel kernels
+
+    int32_t n = 0;
+    int ld = 0;
+    int64_t nf = 0, m = 0, nnz = 0;
+
+    int *d_rp = nullptr, *d_col = nullptr, *d_eid = nullptr;
+    double *d_val = nullptr, *d_diag = nullptr, *d_ew = nullptr;
+    int *d_ci = nullptr, *d_cj = nullptr;
+    double *d_kappa = nullptr, *d_x = nullptr, *d_g = nullptr, *d_tmp_m = nullptr;
+    uint8_t* d_sel = nullptr;
+    double *d_v = nullptr, *d_y = nullptr, *d_x0 = nullptr, *d_tmp_n = nullptr;
+    double x0_norm = 0.0;
+
+    // Lanczos
+    double* d_basis = nullptr;
+    int64_t basis_cap = 0;  // number of Lanczos steps the basis can hold (cap + 1 vectors)
+    double *d_alpha = nullptr, *d_beta = nullptr, *d_ysum = nullptr, *d_usum = nullptr, *d_coef = nullptr;
+    LzScalars* d_sc = nullptr;
+    double *h_alpha = nullptr, *h_beta = nullptr;  // pinned
+    LzScalars* h_sc = nullptr;                     // pinned
+    cudaGraphExec_t lz_graph = nullptr;
+
+    // reductions / selection
+    double* d_partials = nullptr;
+    unsigned int* d_counter = nullptr;
+    SelState* d_sel_state = nullptr;
+    unsigned int* d_blockcnt = nullptr;
+    SelState* h_sel_state = nullptr;  // pinned
+    cudaGraphExec_t sel_graph = nullptr;
+
+    void* d_flush = nullptr;
+
+    bool have_x = false, have_v = false, have_g = false, have_sel = false;
+    double lnorm = 0.0;
+    int64_t nnz_active = 0;
+    double min_sel_tol = 1e-10;
+
+    int64_t c_launches = 0, c_spmv = 0, c_steps = 0, c_solves = 0;
+    double phase_ms[MACB_T_COUNT] = {0, 0, 0, 0, 0, 0};
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    std::string err;
+
+    ReduceWS ws() const { return ReduceWS{d_partials, d_counter}; }
+    int grid_for(int64_t work_items) const {
+        int64_t b = (work_items + kBlock - 1) / kBlock;
+        if (b < 1) b = 1;
+        return (int)std::min<int64_t>(b, grid_max);
+    }
+    int grid_rows() const { return grid_for((int64_t)n * W); }
+};
+
+namespace {
+
+struct PhaseTimer {
+    macb_ctx* c;
+    int phase;
+    PhaseTimer(macb_ctx* c_, int p) : c(c_), phase(p) {
+        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~PhaseTimer() {
+        if (c->profile) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->phase_ms[phase] += ms;
+        }
+    }
+};
+
+int pick_width(double avg_row) {
+    const char* env = getenv("MACB_SPMV_W");
+    if (env) {
+        int w = atoi(env);
+        if (w == 2 || w == 4 || w == 8 || w == 16 || w == 32) return w;
+    }
+    if (avg_row <= 3.0) return 2;
+    if (avg_row <= 8.0) return 4;
+    if (avg_row <= 28.0) return 8;
+    if (avg_row <= 64.0) return 16;
+    return 32;
+}
+
+#define DISPATCH_W(W_, ...)                   \
+    switch (W_) {                             \
+        case 2: { constexpr int WW = 2; __VA_ARGS__; } break;   \
+        case 4: { constexpr int WW = 4; __VA_ARGS__; } break;   \
+        case 8: { constexpr int WW = 8; __VA_ARGS__; } break;   \
+        case 16: { constexpr int WW = 16; __VA_ARGS__; } break; \
+        default: { constexpr int WW = 32; __VA_ARGS__; } break; \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// Host pattern builder: union pattern, off-diagonals only, rows sorted by (column, edge id).
+void build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, int64_t m, const int32_t* ci,
+                   const int32_t* cj, std::vector<int32_t>& rp, std::vector<int32_t>& col, std::vector<int32_t>& eid) {
+    const int64_t ne = nf + m;
+    auto EI = [&](int64_t e) { return e < nf ? fi[e] : ci[e - nf]; };
+    auto EJ = [&](int64_t e) { return e < nf ? fj[e] : cj[e - nf]; };
+    std::vector<int64_t> cnt((size_t)n + 1, 0);
+    int64_t nnz = 0;
+    for (int64_t e = 0; e < ne; ++e) {
+        int32_t a = EI(e), b = EJ(e);
+        if (a < 0 || a >= n || b < 0 || b >= n) throw ArgFail{"edge endpoint out of range [0, num_nodes)", MACB_ERR_ARG};
+        if (a == b) continue;
+        cnt[a + 1]++;
+        cnt[b + 1]++;
+        nnz += 2;
+    }
+    if (nnz >= (int64_t)std::numeric_limits<int32_t>::max()) throw ArgFail{"pattern exceeds int32 slots", MACB_ERR_ARG};
+    // pass 1: bucket by column (so that the stable pass 2 leaves rows sorted by column, then edge id)
+    std::vector<int64_t> cstart((size_t)n + 1, 0);
+    for (int32_t i = 0; i < n; ++i) cstart[i + 1] = cstart[i] + cnt[i + 1];  // symmetric: column counts == row counts
+    std::vector<int32_t> t_row((size_t)nnz), t_eid((size_t)nnz);
+    {
+        std::vector<int64_t> pos(cstart.begin(), cstart.end() - 1);
+        for (int64_t e = 0; e < ne; ++e) {
+            int32_t a = EI(e), b = EJ(e);
+            if (a == b) continue;
+            // entry (row a, col b) goes to column bucket b; entry (row b, col a) to bucket a
+            int64_t p = pos[b]++;
+            t_row[p] = a;
+            t_eid[p] = (int32_t)e;
+            p = pos[a]++;
+            t_row[p] = b;
+            t_eid[p] = (int32_t)e;
+        }
+    }
+    rp.assign((size_t)n + 1, 0);
+    for (int32_t i = 0; i < n; ++i) rp[i + 1] = (int32_t)(rp[i] + cnt[i + 1]);
+    col.resize((size_t)nnz);
+    eid.resize((size_t)nnz);
+    {
+        std::vector<int64_t> pos((size_t)n);
+        for (int32_t i = 0; i < n; ++i) pos[i] = rp[i];
+        for (int32_t c = 0; c < n; ++c)
+            for (int64_t p = cstart[c]; p < cstart[c + 1]; ++p) {
+                int64_t q = pos[t_row[p]]++;
+                col[q] = c;
+                eid[q] = t_eid[p];
+            }
+    }
+}
+
+void free_all(macb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->lz_graph) cudaGraphExecDestroy(c->lz_graph);
+    if (c->sel_graph) cudaGraphExecDestroy(c->sel_graph);
+    void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
+                     c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
+                     c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
+                     c->d_sel_state, c->d_blockcnt, c->d_flush};
+    for (void* p : dptrs)
+        if (p) cudaFree(p);
+    if (c->h_alpha) cudaFreeHost(c->h_alpha);
+    if (c->h_beta) cudaFreeHost(c->h_beta);
+    if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// Deterministic built-in start vector (used when the caller supplies none): splitmix64 + Box-Muller.
+void default_start(int32_t n, std::vector<double>& x0) {
+    x0.resize(n);
+    uint64_t s = 0x9E3779B97F4A7C15ull * 7ull;
+    auto next = [&]() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (int32_t i = 0; i < n; ++i) {
+        double u1 = ((next() >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+        double u2 = (next() >> 11) * (1.0 / 9007199254740992.0);
+        x0[i] = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    }
+}
+
+void upload_start(macb_ctx* c, const double* x0_in) {
+    std::vector<double> x0(c->n);
+    if (x0_in)
+        std::copy(x0_in, x0_in + c->n, x0.begin());
+    else
+        default_start(c->n, x0);
+    // project out the all-ones vector (nx:206-210,230) once on the host
+    long double s = 0.0L;
+    for (double v : x0) s += v;
+    double mean = (double)(s / c->n);
+    long double q = 0.0L;
+    for (double& v : x0) {
+        v -= mean;
+        q += (long double)v * v;
+    }
+    c->x0_norm = std::sqrt((double)q);
+    if (c->n >= 2 && !(c->x0_norm > 0.0))
+        throw ArgFail{"start vector is constant (no component orthogonal to 1)", MACB_ERR_ARG};
+    CK(cudaMemcpyAsync(c->d_x0, x0.data(), sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+void launch_assemble(macb_ctx* c) {
+    PhaseTimer pt(c, MACB_T_ASSEMBLE);
+    const int grid = c->grid_rows();
+    DISPATCH_W(c->W, k_assemble<WW><<<grid, kBlock, 0, c->stream>>>(c->n, c->d_rp, c->d_eid, c->d_ew, c->d_val,
+                                                                       c->d_diag, c->d_sc, c->ws()));
+    CK(cudaGetLastError());
+    c->c_launches++;
+    CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->lnorm = c->h_sc->lnorm;
+    c->nnz_active = c->h_sc->nnz_active;
+    c->have_v = false;
+    c->have_g = false;
+    c->have_sel = false;
+}
+
+template <int MODE>
+void launch_spmv(macb_ctx* c, const double* x, double* y) {
+    SpmvArgs a;
+    a.n = c->n;
+    a.ld = c->ld;
+    a.rp = c->d_rp;
+    a.col = c->d_col;
+    a.val = c->d_val;
+    a.diag = c->d_diag;
+    a.x = x;
+    a.y = y;
+    a.sc = c->d_sc;
+    a.alpha = c->d_alpha;
+    a.beta = c->d_beta;
+    a.ysum = c->d_ysum;
+    a.ws = c->ws();
+    const int grid = c->grid_rows();
+    DISPATCH_W(c->W, k_spmv<WW, MODE><<<grid, kBlock, 0, c->stream>>>(a));
+    CK(cudaGetLastError());
+}
+
+void launch_lanczos_step(macb_ctx* c) {
+    launch_spmv<1>(c, c->d_basis, c->d_y);
+    k_lanczos_b<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, c->d_basis, c->d_y, c->d_alpha, c->d_beta,
+                                                             c->d_ysum, c->d_usum, c->d_sc, c->ws());
+    CK(cudaGetLastError());
+}
+
+void ensure_basis(macb_ctx* c, int max_steps) {
+    if (c->d_basis) return;
+    double gb = 8.0;
+    if (const char* env = getenv("MACB_BASIS_GB")) gb = atof(env);
+    int64_t by_mem = (int64_t)(gb * 1073741824.0 / (8.0 * c->ld)) - 1;
+    int64_t cap = std::max<int64_t>(2 * kGraphSteps, std::min<int64_t>(by_mem, 65536));
+    cap = (cap / kGraphSteps) * kGraphSteps;
+    (void)max_steps;
+    c->basis_cap = cap;
+    c->d_basis = dalloc<double>((size_t)(cap + 1) * c->ld);
+    c->d_alpha = dalloc<double>(cap + 1);
+    c->d_beta = dalloc<double>(cap + 2);
+    c->d_ysum = dalloc<double>(cap + 1);
+    c->d_usum = dalloc<double>(cap + 2);
+    c->d_coef = dalloc<double>(cap + 1);
+    CK(cudaMallocHost(&c->h_alpha, sizeof(double) * (cap + 1)));
+    CK(cudaMallocHost(&c->h_beta, sizeof(double) * (cap + 2)));
+    // capture kGraphSteps Lanczos steps (2 kernels each) into one graph
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    for (int s = 0; s < kGraphSteps; ++s) launch_lanczos_step(c);
+    CK(cudaStreamEndCapture(c->stream, &g));
+    CK(cudaGraphInstantiate(&c->lz_graph, g, 0));
+    CK(cudaGraphDestroy(g));
+}
+
+void run_lanczos_steps(macb_ctx* c, int nsteps) {
+    int done = 0;
+    while (nsteps - done >= kGraphSteps) {
+        CK(cudaGraphLaunch(c->lz_graph, c->stream));
+        done += kGraphSteps;
+    }
+    for (; done < nsteps; ++done) launch_lanczos_step(c);
+    c->c_launches += 2 * (int64_t)nsteps;
+    c->c_spmv += nsteps;
+    c->c_steps += nsteps;
+}
+
+struct FiedlerResult {
+    double lambda2 = 0.0, resid = 0.0;
+    int steps = 0;
+    bool converged = false;
+};
+
+// Ritz vector of T_k -> d_v (unit norm, zero mean), true residual test of nx:243.
+void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResult& out) {
+    std::vector<double> coef(k);
+    for (int t = 0; t < k; ++t) coef[t] = s[t] / c->h_beta[t];
+    CK(cudaMemcpyAsync(c->d_coef, coef.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
+    k_ritz<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws());
+    k_center_normalize<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_sc);
+    launch_spmv<2>(c, c->d_v, c->d_y);
+    k_resid_l1<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_y, c->d_sc, c->ws());
+    CK(cudaGetLastError());
+    c->c_launches += 4;
+    c->c_spmv += 1;
+    CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // also keeps `coef` alive until the copy is done
+    out.lambda2 = c->h_sc->vLv / c->h_sc->vv;
+    out.resid = c->h_sc->res1 / (std::sqrt(c->h_sc->vv) * c->lnorm);
+}
+
+// Deflated Lanczos on P L(x) P.  Replaces nx:149-253 (see macb200.h).
+int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult& out) {
+    if (!c->have_x) throw ArgFail{"macb_fiedler: call macb_set_x first", MACB_ERR_STATE};
+    if (c->n < 2) throw ArgFail{"macb_fiedler: need at least 2 nodes", MACB_ERR_ARG};
+    if (max_steps <= 0) max_steps = 20000;
+    PhaseTimer pt(c, MACB_T_FIEDLER);
+    ensure_basis(c, max_steps);
+    c->c_solves++;
+    const int n = c->n;
+    const double sqrtn = std::sqrt((double)n);
+    const double lnorm = c->lnorm;
+    if (!(lnorm > 0.0)) {  // empty graph: every vector orthogonal to 1 is a null vector
+        CK(cudaMemcpyAsync(c->d_v, c->d_x0, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        out = FiedlerResult{};
+        out.converged = true;
+        c->have_v = true;
+        return MACB_OK;
+    }
+    const double brk = 1e-13 * lnorm;
+
+    bool use_warm = warm && c->have_v;
+    int total_steps = 0;
+    std::vector<double> s;
+    for (int restart = 0; restart < 64; ++restart) {
+        // ---- (re)start
+        const double* src = use_warm ? c->d_v : c->d_x0;
+        CK(cudaMemcpyAsync(c->d_basis, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        k_set_lanczos_start<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_beta, c->d_usum, use_warm ? 1.0 : c->x0_norm);
+        c->c_launches++;
+        c->h_beta[0] = use_warm ? 1.0 : c->x0_norm;
+        int k_done = 0;
+        double theta_prev = std::numeric_limits<double>::infinity();
+        // no cap at n - 1: without re-orthogonalisation the recurrence simply keeps refining (ghost
+        // copies appear in T_k); a genuinely exhausted Krylov space shows up as beta ~ 0 below.
+        const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)(max_steps - total_steps));
+        bool invariant = false;
+        while (true) {
+            int batch;
+            if (k_done < 4 * kGraphSteps)
+                batch = kGraphSteps;
+            else
+                batch = std::min(16 * kGraphSteps, ((k_done / 4) / kGraphSteps) * kGraphSteps);
+            batch = std::min(batch, k_limit - k_done);
+            if (batch > 0) {
+                run_lanczos_steps(c, batch);
+                CK(cudaMemcpyAsync(c->h_alpha + k_done, c->d_alpha + k_done, sizeof(double) * batch, cudaMemcpyDeviceToHost,
+                                   c->stream));
+                CK(cudaMemcpyAsync(c->h_beta + k_done + 1, c->d_beta + k_done + 1, sizeof(double) * batch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                k_done += batch;
+                total_steps += batch;
+            }
+            // breakdown: beta[j] ~ 0 => span(u_0..u_{j-1}) is invariant and T_j is exact
+            int k = k_done;
+            for (int j = 1; j <= k_done; ++j)
+                if (!(c->h_beta[j] > brk)) {
+                    k = j;
+                    invariant = true;
+                    break;
+                }
+            if (k == 0) throw ArgFail{"macb_fiedler: Lanczos made no progress", MACB_ERR_STATE};
+            const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k, invariant ? std::numeric_limits<double>::infinity() : theta_prev);
+            s.resize(k);
+            tridiag_vector(c->h_alpha, c->h_beta, k, theta, s.data());
+            theta_prev = theta;
+            const double est = std::fabs(c->h_beta[k]) * std::fabs(s[k - 1]);
+            const bool exhausted = invariant || k_done >= k_limit;
+            if (est * sqrtn < tol * lnorm || exhausted) {
+                finalize_ritz(c, k, s, out);
+                out.steps = total_steps;
+                if (out.resid < tol) {
+                    out.converged = true;
+                    c->have_v = true;
+                    return MACB_OK;
+                }
+                if (exhausted) break;  // restart from the best Ritz vector (now in d_v)
+            }
+        }
+        c->have_v = true;
+        use_warm = true;  // explicit restart from the current Ritz vector
+        if (total_steps >= max_steps) break;
+        if (invariant) break;  // T_k was exact and still missed tol: tol is below what double precision resolves
+    }
+    out.steps = total_steps;
+    return MACB_NOT_CONVERGED;
+}
+
+void launch_gradient(macb_ctx* c) {
+    if (!c->have_v) throw ArgFail{"macb_gradient: call macb_fiedler first", MACB_ERR_STATE};
+    PhaseTimer pt(c, MACB_T_GRADIENT);
+    if (c->m > 0) {
+        k_gradient<<<c->grid_for(c->m), kBlock, 0, c->stream>>>(c->m, c->d_ci, c->d_cj, c->d_kappa, c->d_v, c->d_x, c->d_g,
+                                                                c->d_sc, c->ws());
+        CK(cudaGetLastError());
+        c->c_launches++;
+    }
+    c->have_g = true;
+    c->have_sel = false;
+}
+
+// radix-select passes over `g` (device, length m) + selection mask into `sel`; dual term into sc
+void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel) {
+    PhaseTimer pt(c, MACB_T_TOPK);
+    const int64_t m = c->m;
+    const int grid = c->grid_for(m);
+    k_sel_init<<<1, kBlock, 0, c->stream>>>(c->d_sel_state, (long long)k);
+    c->c_launches++;
+    if (k > 0) {
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            k_sel_hist<<<grid, kBlock, 0, c->stream>>>(m, g, c->d_sel_state, shift);
+            k_sel_pick<<<1, kBlock, 0, c->stream>>>(c->d_sel_state, shift);
+        }
+        c->c_launches += 16;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_sel_state, c->d_sel_state, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int64_t chunk = (m + grid - 1) / grid;
+    chunk = ((chunk + kBlock - 1) / kBlock) * kBlock;
+    const int nblocks = (int)((m + chunk - 1) / chunk);
+    const bool ranked = k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining;
+    if (ranked) {
+        k_sel_tie_count<<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, c->d_sel_state, c->d_blockcnt);
+        k_sel_tie_scan<<<1, 32, 0, c->stream>>>(nblocks, c->d_blockcnt);
+        k_sel_apply<true><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, c->d_sel_state, c->d_blockcnt, sel, c->d_sc, c->ws());
+        c->c_launches += 3;
+    } else {
+        k_sel_apply<false><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, c->d_sel_state, c->d_blockcnt, sel, c->d_sc, c->ws());
+        c->c_launches += 1;
+    }
+    CK(cudaGetLastError());
+}
+
+void set_x_device(macb_ctx* c, double tol) {
+    // d_x already holds x
+    c->min_sel_tol = tol;
+    if (c->m > 0) {
+        k_edge_weights<<<c->grid_for(c->m), kBlock, 0, c->stream>>>(c->m, c->d_x, c->d_kappa, tol, c->d_ew + c->nf);
+        CK(cudaGetLastError());
+        c->c_launches++;
+    }
+    launch_assemble(c);
+    c->have_x = true;
+}
+
+template <typename F>
+int guarded(macb_ctx* c, F&& f) {
+    if (!c) return MACB_ERR_ARG;
+    try {
+        CK(cudaSetDevice(c->device));
+        return f();
+    } catch (const CudaFail& e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at api.cu:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
+        c->err = buf;
+        cudaGetLastError();
+        return MACB_ERR_CUDA;
+    } catch (const ArgFail& e) {
+        c->err = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        c->err = "host allocation failed";
+        return MACB_ERR_NOMEM;
+    }
+}
+
+}  // namespace
+
+// ================================================================================================ C-ABI
+extern "C" {
+
+const char* macb_version(void) { return "macb200 0.1.0 (sm_100a)"; }
+
+const char* macb_last_error(macb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int macb_host_build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, int64_t m, const int32_t* ci,
+                            const int32_t* cj, int32_t* row_ptr, int32_t* col, int32_t* eid, int64_t* nnz) {
+    try {
+        std::vector<int32_t> rp, cc, ee;
+        build_pattern(n, nf, fi, fj, m, ci, cj, rp, cc, ee);
+        if (row_ptr) std::copy(rp.begin(), rp.end(), row_ptr);
+        if (col) std::copy(cc.begin(), cc.end(), col);
+        if (eid) std::copy(ee.begin(), ee.end(), eid);
+        if (nnz) *nnz = (int64_t)cc.size();
+        return MACB_OK;
+    } catch (const ArgFail& e) {
+        g_create_error = e.msg;
+        return e.code;
+    }
+}
+
+int macb_tridiag_smallest(const double* a, const double* b, int k, double* theta, double* s) {
+    if (!a || !b || k <= 0) return MACB_ERR_ARG;
+    double th = tridiag_smallest_value(a, b, k, std::numeric_limits<double>::infinity());
+    if (theta) *theta = th;
+    if (s) tridiag_vector(a, b, k, th, s);
+    return MACB_OK;
+}
+
+int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, const double* fw, int64_t m,
+                const int32_t* ci, const int32_t* cj, const double* ckappa, int device, macb_handle* out) {
+    if (!out) return MACB_ERR_ARG;
+    *out = nullptr;
+    if (n < 1 || nf < 0 || m < 0 || nf + m >= (int64_t)std::numeric_limits<int32_t>::max()) {
+        g_create_error = "macb_create: bad sizes";
+        return MACB_ERR_ARG;
+    }
+    macb_ctx* c = new macb_ctx();
+    try {
+        if (device < 0) CK(cudaGetDevice(&device));
+        c->device = device;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        c->grid_max = c->sm_count * (2048 / kBlock);
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev0));
+        CK(cudaEventCreate(&c->ev1));
+        c->n = n;
+        c->ld = ((n + 31) / 32) * 32;
+        c->nf = nf;
+        c->m = m;
+
+        std::vector<int32_t> rp, col, eid;
+        build_pattern(n, nf, fi, fj, m, ci, cj, rp, col, eid);
+        c->nnz = (int64_t)col.size();
+        c->W = pick_width((double)c->nnz / std::max(1, n));
+
+        c->d_rp = dalloc<int>(n + 1);
+        c->d_col = dalloc<int>(c->nnz);
+        c->d_eid = dalloc<int>(c->nnz);
+        c->d_val = dalloc<double>(c->nnz);
+        c->d_diag = dalloc<double>(n);
+        c->d_ew = dalloc<double>(nf + m);
+        c->d_ci = dalloc<int>(m);
+        c->d_cj = dalloc<int>(m);
+        c->d_kappa = dalloc<double>(m);
+        c->d_x = dalloc<double>(m);
+        c->d_g = dalloc<double>(m);
+        c->d_tmp_m = dalloc<double>(m);
+        c->d_sel = dalloc<uint8_t>(m);
+        c->d_v = dalloc<double>(c->ld);
+        c->d_y = dalloc<double>(c->ld);
+        c->d_x0 = dalloc<double>(c->ld);
+        c->d_tmp_n = dalloc<double>(c->ld);
+        c->d_sc = dalloc<LzScalars>(1);
+        c->d_partials = dalloc<double>((size_t)c->grid_max * 8);
+        c->d_counter = dalloc<unsigned int>(8);
+        c->d_sel_state = dalloc<SelState>(1);
+        c->d_blockcnt = dalloc<unsigned int>(c->grid_max + 8);
+        CK(cudaMallocHost(&c->h_sc, sizeof(LzScalars)));
+        CK(cudaMallocHost(&c->h_sel_state, sizeof(SelState)));
+        CK(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(unsigned int), c->stream));
+        CK(cudaMemsetAsync(c->d_sc, 0, sizeof(LzScalars), c->stream));
+        CK(cudaMemsetAsync(c->d_x, 0, sizeof(double) * std::max<int64_t>(m, 1), c->stream));
+        CK(cudaMemsetAsync(c->d_ew, 0, sizeof(double) * std::max<int64_t>(nf + m, 1), c->stream));
+
+        CK(cudaMemcpyAsync(c->d_rp, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+        if (c->nnz) {
+            CK(cudaMemcpyAsync(c->d_col, col.data(), sizeof(int) * c->nnz, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_eid, eid.data(), sizeof(int) * c->nnz, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (nf) CK(cudaMemcpyAsync(c->d_ew, fw, sizeof(double) * nf, cudaMemcpyHostToDevice, c->stream));
+        if (m) {
+            CK(cudaMemcpyAsync(c->d_ci, ci, sizeof(int) * m, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_cj, cj, sizeof(int) * m, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_kappa, ckappa, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        upload_start(c, nullptr);
+    } catch (const CudaFail& e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "macb_create: CUDA error %d (%s) at api.cu:%d: %s", (int)e.e, cudaGetErrorString(e.e),
+                 e.line, e.what);
+        g_create_error = buf;
+        cudaGetLastError();
+        free_all(c);
+        return MACB_ERR_CUDA;
+    } catch (const ArgFail& e) {
+        g_create_error = "macb_create: " + e.msg;
+        free_all(c);
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_create_error = "macb_create: host allocation failed";
+        free_all(c);
+        return MACB_ERR_NOMEM;
+    }
+    *out = c;
+    return MACB_OK;
+}
+
+int macb_destroy(macb_handle h) {
+    if (!h) return MACB_OK;
+    free_all(h);
+    return MACB_OK;
+}
+
+int macb_set_x(macb_handle h, const double* x, double min_sel_tol) {
+    return guarded(h, [&]() {
+        if (!x && h->m > 0) throw ArgFail{"macb_set_x: x is NULL", MACB_ERR_ARG};
+        {
+            PhaseTimer pt(h, MACB_T_COPY);
+            if (h->m) CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->m, cudaMemcpyHostToDevice, h->stream));
+        }
+        set_x_device(h, min_sel_tol);
+        return (int)MACB_OK;
+    });
+}
+
+int macb_get_x(macb_handle h, double* x) {
+    return guarded(h, [&]() {
+        if (h->m) CK(cudaMemcpyAsync(x, h->d_x, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_spmv(macb_handle h, const double* v, double* y) {
+    return guarded(h, [&]() {
+        if (!h->have_x) throw ArgFail{"macb_spmv: call macb_set_x first", MACB_ERR_STATE};
+        if (!v || !y) throw ArgFail{"macb_spmv: NULL vector", MACB_ERR_ARG};
+        CK(cudaMemcpyAsync(h->d_tmp_n, v, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+        launch_spmv<0>(h, h->d_tmp_n, h->d_y);
+        h->c_launches++;
+        h->c_spmv++;
+        CK(cudaMemcpyAsync(y, h->d_y, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_lnorm(macb_handle h, double* lnorm) {
+    return guarded(h, [&]() {
+        if (!h->have_x) throw ArgFail{"macb_lnorm: call macb_set_x first", MACB_ERR_STATE};
+        if (lnorm) *lnorm = h->lnorm;
+        return (int)MACB_OK;
+    });
+}
+
+int macb_set_start(macb_handle h, const double* x0) {
+    return guarded(h, [&]() {
+        upload_start(h, x0);
+        return (int)MACB_OK;
+    });
+}
+
+int macb_fiedler(macb_handle h, double tol, int max_steps, int warm, double* lambda2, double* v, int* steps,
+                 double* resid) {
+    return guarded(h, [&]() {
+        FiedlerResult r;
+        int rc = run_fiedler(h, tol, max_steps, warm, r);
+        if (lambda2) *lambda2 = r.lambda2;
+        if (steps) *steps = r.steps;
+        if (resid) *resid = r.resid;
+        if (v) {
+            PhaseTimer pt(h, MACB_T_COPY);
+            CK(cudaMemcpyAsync(v, h->d_v, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        if (rc == MACB_NOT_CONVERGED) h->err = "macb_fiedler: eigen-iteration did not reach tol within max_steps";
+        return rc;
+    });
+}
+
+int macb_gradient(macb_handle h, double* g) {
+    return guarded(h, [&]() {
+        launch_gradient(h);
+        if (g && h->m) {
+            PhaseTimer pt(h, MACB_T_COPY);
+            CK(cudaMemcpyAsync(g, h->d_g, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_topk(macb_handle h, int64_t k, double* s) {
+    return guarded(h, [&]() {
+        if (!h->have_g) throw ArgFail{"macb_topk: call macb_gradient first", MACB_ERR_STATE};
+        if (k < 0 || k > h->m) throw ArgFail{"macb_topk: k out of range", MACB_ERR_ARG};
+        launch_topk(h, h->d_g, h->d_x, k, h->d_sel);
+        h->have_sel = true;
+        if (s && h->m) {
+            k_mask_to_double<<<h->grid_for(h->m), kBlock, 0, h->stream>>>(h->m, h->d_sel, h->d_tmp_m);
+            h->c_launches++;
+            CK(cudaMemcpyAsync(s, h->d_tmp_m, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s) {
+    if (!g || !s || m < 1 || k < 0 || k > m) {
+        g_create_error = "macb_topk_dense: bad arguments";
+        return MACB_ERR_ARG;
+    }
+    // A throw-away handle over an edgeless 1-node... the LP oracle needs only the candidate arrays.
+    std::vector<int32_t> zi((size_t)m, 0);
+    std::vector<double> zk((size_t)m, 0.0);
+    macb_handle h = nullptr;
+    int rc = macb_create(1, 0, nullptr, nullptr, nullptr, m, zi.data(), zi.data(), zk.data(), device, &h);
+    if (rc != MACB_OK) return rc;
+    rc = guarded(h, [&]() {
+        CK(cudaMemcpyAsync(h->d_g, g, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+        launch_topk(h, h->d_g, h->d_x, k, h->d_sel);
+        k_mask_to_double<<<h->grid_for(m), kBlock, 0, h->stream>>>(m, h->d_sel, h->d_tmp_m);
+        CK(cudaMemcpyAsync(s, h->d_tmp_m, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+    if (rc != MACB_OK) g_create_error = h->err;
+    macb_destroy(h);
+    return rc;
+}
+
+int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, double rel_gap_tol, double grad_norm_tol,
+                double fiedler_tol, double min_sel_tol, int fiedler_max_steps, int warm, double* w, double* u_out,
+                int* iters_done, double* f_hist, double* u_hist) {
+    return guarded(h, [&]() {
+        if (!x_init && h->m > 0) throw ArgFail{"macb_fw_run: x_init is NULL", MACB_ERR_ARG};
+        if (k < 0 || k > h->m) throw ArgFail{"macb_fw_run: k out of range", MACB_ERR_ARG};
+        {
+            PhaseTimer pt(h, MACB_T_COPY);
+            if (h->m) CK(cudaMemcpyAsync(h->d_x, x_init, sizeof(double) * h->m, cudaMemcpyHostToDevice, h->stream));
+        }
+        h->min_sel_tol = min_sel_tol;
+        if (h->m > 0) {
+            k_edge_weights<<<h->grid_for(h->m), kBlock, 0, h->stream>>>(h->m, h->d_x, h->d_kappa, min_sel_tol, h->d_ew + h->nf);
+            h->c_launches++;
+        }
+        double u = std::numeric_limits<double>::infinity();
+        int status = MACB_OK;
+        int it = 0;
+        for (; it < max_iters; ++it) {
+            launch_assemble(h);  // L(x)                          mac.py:115 -> :74
+            h->have_x = true;
+            FiedlerResult fr;    // f, v                          mac.py:115 -> fiedler.py:9
+            int rc = run_fiedler(h, fiedler_tol, fiedler_max_steps, warm && it > 0, fr);
+            if (rc == MACB_NOT_CONVERGED) status = MACB_NOT_CONVERGED;
+            launch_gradient(h);  // g                             mac.py:117-124
+            launch_topk(h, h->d_g, h->d_x, k, h->d_sel);  // s    frankwolfe.py:58
+            CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            const double f = fr.lambda2;
+            u = std::min(u, f + h->h_sc->gs_minus_x);  //         frankwolfe.py:62
+            if (f_hist) f_hist[it] = f;
+            if (u_hist) u_hist[it] = u;
+            if (std::sqrt(h->h_sc->gnorm2) < grad_norm_tol) {  // frankwolfe.py:65
+                ++it;
+                break;
+            }
+            if ((u - f) < rel_gap_tol * std::fabs(f)) {  //       frankwolfe.py:71
+                ++it;
+                break;
+            }
+            {
+                PhaseTimer pt(h, MACB_T_UPDATE);
+                const double gamma = 2.0 / ((double)it + 2.0);  // frankwolfe.py:7-8,76
+                if (h->m > 0) {
+                    k_fw_update<<<h->grid_for(h->m), kBlock, 0, h->stream>>>(h->m, gamma, h->d_sel, h->d_kappa, min_sel_tol,
+                                                                            h->d_x, h->d_ew + h->nf);
+                    CK(cudaGetLastError());
+                    h->c_launches++;
+                }
+            }
+        }
+        // the loop leaves L(x) stale with respect to d_x if it ran to max_iters; mark state accordingly
+        h->have_x = false;
+        h->have_v = false;
+        h->have_g = false;
+        if (iters_done) *iters_done = it;
+        if (u_out) *u_out = u;
+        if (w && h->m) {
+            PhaseTimer pt(h, MACB_T_COPY);
+            CK(cudaMemcpyAsync(w, h->d_x, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        if (status == MACB_NOT_CONVERGED) h->err = "macb_fw_run: an eigen-solve did not reach tol within fiedler_max_steps";
+        return status;
+    });
+}
+
+int macb_counters(macb_handle h, int64_t* kernel_launches, int64_t* spmv_launches, int64_t* lanczos_steps,
+                  int64_t* fiedler_solves, double* phase_ms) {
+    if (!h) return MACB_ERR_ARG;
+    if (kernel_launches) *kernel_launches = h->c_launches;
+    if (spmv_launches) *spmv_launches = h->c_spmv;
+    if (lanczos_steps) *lanczos_steps = h->c_steps;
+    if (fiedler_solves) *fiedler_solves = h->c_solves;
+    if (phase_ms)
+        for (int i = 0; i < MACB_T_COUNT; ++i) phase_ms[i] = h->phase_ms[i];
+    return MACB_OK;
+}
+
+int macb_reset_counters(macb_handle h) {
+    if (!h) return MACB_ERR_ARG;
+    h->c_launches = h->c_spmv = h->c_steps = h->c_solves = 0;
+    for (int i = 0; i < MACB_T_COUNT; ++i) h->phase_ms[i] = 0.0;
+    return MACB_OK;
+}
+
+int macb_set_profile(macb_handle h, int on) {
+    if (!h) return MACB_ERR_ARG;
+    h->profile = on != 0;
+    return MACB_OK;
+}
+
+int macb_sizes(macb_handle h, int64_t* n, int64_t* m, int64_t* nnz_union, int64_t* nnz_active) {
+    if (!h) return MACB_ERR_ARG;
+    if (n) *n = h->n;
+    if (m) *m = h->m;
+    if (nnz_union) *nnz_union = h->nnz;
+    if (nnz_active) *nnz_active = h->nnz_active;
+    return MACB_OK;
+}
+
+int macb_l2_flush(macb_handle h) {
+    return guarded(h, [&]() {
+        if (!h->d_flush) CK(cudaMalloc(&h->d_flush, kFlushBytes));
+        CK(cudaMemsetAsync(h->d_flush, 0xA5, kFlushBytes, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_spmv_bench(macb_handle h, int reps, int flush_l2, double* avg_ms, double* algo_bytes) {
+    return guarded(h, [&]() {
+        if (!h->have_x) throw ArgFail{"macb_spmv_bench: call macb_set_x first", MACB_ERR_STATE};
+        if (reps < 1) reps = 1;
+        CK(cudaMemcpyAsync(h->d_tmp_n, h->d_x0, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+        for (int i = 0; i < 3; ++i) launch_spmv<0>(h, h->d_tmp_n, h->d_y);
+        double total = 0.0;
+        if (flush_l2) {
+            if (!h->d_flush) CK(cudaMalloc(&h->d_flush, kFlushBytes));
+            for (int i = 0; i < reps; ++i) {
+                CK(cudaMemsetAsync(h->d_flush, i, kFlushBytes, h->stream));
+                CK(cudaEventRecord(h->ev0, h->stream));
+                launch_spmv<0>(h, h->d_tmp_n, h->d_y);
+                CK(cudaEventRecord(h->ev1, h->stream));
+                CK(cudaEventSynchronize(h->ev1));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+                total += ms;
+            }
+        } else {
+            CK(cudaEventRecord(h->ev0, h->stream));
+            for (int i = 0; i < reps; ++i) launch_spmv<0>(h, h->d_tmp_n, h->d_y);
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaEventSynchronize(h->ev1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            total = ms;
+        }
+        h->c_launches += reps + 3;
+        h->c_spmv += reps + 3;
+        if (avg_ms) *avg_ms = total / reps;
+        // nnz (8 + 4) + (n + 1) 4 + 8 n (x) + 8 n (y); the diagonal counts as n more non-zeros
+        if (algo_bytes) *algo_bytes = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n;
+        return (int)MACB_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,562 @@
+// sm_100a device kernels for the MAC Frank-Wolfe hot path.  All arithmetic is IEEE double.
+//
+// Data layout in HBM (all arrays live for the lifetime of a handle):
+//   pattern   row_ptr[n+1], col[nnz], eid[nnz]    union pattern of L(w), off-diagonals only
+//   values    val[nnz] (>= 0, the edge weight w_e), diag[n] (weighted degree)   rewritten per FW step
+//   edges     ew[nf+m]  current weight of every edge (fixed: constant; candidate k: x_k kappa_k)
+//             ci[m], cj[m], kappa[m], x[m], g[m], sel[m] (u8)
+//   Lanczos   basis[(cap+1) * ld]  un-normalised Lanczos vectors u_j (row j), ld = n padded to 32
+//             alpha[cap], beta[cap+1] (beta[j] = ||u_j||), ysum[cap]
+// L(w) v is evaluated as  y_i = diag_i v_i - sum_s val_s v[col_s]  (the Laplacian of the reference,
+// graphs.py:77-96, with the duplicate-summed diagonal kept as a separate array).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace macb {
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+// Scalars shared between the kernels of one eigen-solve (device memory).
+struct LzScalars {
+    int step;          // index j of the Lanczos vector the next A-kernel multiplies
+    int pad;
+    double lnorm;      // max_i sum_j |L_ij|  (nx:229)
+    int64_t nnz_active;
+    // finalisation
+    double ritz_sum, ritz_sq;   // sum y, sum y^2 of the raw Ritz vector
+    double vLv, vv;             // Rayleigh quotient pieces
+    double res1;                // ||L v - theta v||_1
+    // gradient / LP
+    double gnorm2, gdotx, gs_minus_x;
+    int64_t nsel;
+};
+
+struct ReduceWS {
+    double* partials;        // [grid_max * 4]
+    unsigned int* counter;   // zero between kernels
+};
+
+__device__ __forceinline__ double ld_nc(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int ld_nc(const int* p) { return __ldg(p); }
+
+// Streaming (read-once-per-kernel) loads: keep them out of L1 so the gathered vector stays there.
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ double safe_inv(double b) { return (b > 1e-290) ? 1.0 / b : 0.0; }
+
+// ---- block / grid reductions (fixed tree => bitwise reproducible for a fixed grid) ---------------
+template <int NV, bool MAXOP = false>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* sm /*[NV * kWarpsPerBlock]*/) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double t = __shfl_xor_sync(0xffffffffu, v[i], o);
+            v[i] = MAXOP ? fmax(v[i], t) : v[i] + t;
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm[i * kWarpsPerBlock + warp] = v[i];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < kWarpsPerBlock) ? sm[i * kWarpsPerBlock + lane] : (MAXOP ? -1.0e300 : 0.0);
+#pragma unroll
+            for (int o = kWarpsPerBlock / 2; o > 0; o >>= 1) {
+                double t = __shfl_xor_sync(0xffffffffu, x, o);
+                x = MAXOP ? fmax(x, t) : x + t;
+            }
+            v[i] = x;
+        }
+    }
+}
+
+// Every block publishes its partial; the last block to arrive reduces all partials in a fixed
+// order.  Returns true on thread 0 of that last block, with the grand totals in v.
+template <int NV, bool MAXOP = false>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], ReduceWS ws, double* sm, int* sm_flag) {
+    block_reduce<NV, MAXOP>(v, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ws.partials[(size_t)blockIdx.x * NV + i] = v[i];
+        __threadfence();
+        unsigned int t = atomicAdd(ws.counter, 1u);
+        *sm_flag = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*sm_flag) return false;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = MAXOP ? -1.0e300 : 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double t = __ldcg(ws.partials + (size_t)b * NV + i);
+            v[i] = MAXOP ? fmax(v[i], t) : v[i] + t;
+        }
+    block_reduce<NV, MAXOP>(v, sm);
+    if (threadIdx.x == 0) {
+        *ws.counter = 0u;
+        return true;
+    }
+    return false;
+}
+
+// ---- K2: assembly of L(x) on the fixed pattern ----------------------------------------------------
+// ew[nf + k] = x_k kappa_k if x_k > tol else 0   (mac.py:85-86)
+__global__ void __launch_bounds__(kBlock) k_edge_weights(int64_t m, const double* __restrict__ x,
+                                                         const double* __restrict__ kappa, double tol,
+                                                         double* __restrict__ ew_cand) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        double xi = x[i];
+        ew_cand[i] = (xi > tol) ? xi * kappa[i] : 0.0;
+    }
+}
+
+// W lanes per row: val[s] = ew[eid[s]], diag[row] = sum_s val[s]; Lnorm = 2 max diag; active-slot count.
+template <int W>
+__global__ void __launch_bounds__(kBlock) k_assemble(int n, const int* __restrict__ rp, const int* __restrict__ eid,
+                                                     const double* __restrict__ ew, double* __restrict__ val,
+                                                     double* __restrict__ diag, LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    const int lane = threadIdx.x & (W - 1);
+    const int sub = (blockIdx.x * kBlock + threadIdx.x) / W;
+    const int nsub = gridDim.x * kBlock / W;
+    double dmax = 0.0, cnt = 0.0;
+    const int rows_per_warp = 32 / W;
+    for (int base = sub - (sub % rows_per_warp); base < n; base += nsub) {
+        int row = base + (sub % rows_per_warp);
+        double acc = 0.0;
+        if (row < n) {
+            int s0 = rp[row], s1 = rp[row + 1];
+            for (int s = s0 + lane; s < s1; s += W) {
+                double w = ew[ld_stream(eid + s)];
+                val[s] = w;
+                acc += w;
+                cnt += (w != 0.0) ? 1.0 : 0.0;
+            }
+        }
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (row < n && lane == 0) {
+            diag[row] = acc;
+            dmax = fmax(dmax, acc);
+        }
+    }
+    double v[1] = {dmax};
+    bool last_max = grid_reduce<1, true>(v, ws, sm, &flag);
+    if (last_max) sc->lnorm = 2.0 * v[0];
+    // second reduction (count) reuses the workspace after the first has fully completed in this block
+    __syncthreads();
+    double c[1] = {cnt};
+    ReduceWS ws2 = {ws.partials + (size_t)gridDim.x, ws.counter + 1};
+    bool last_cnt = grid_reduce<1, false>(c, ws2, sm, &flag);
+    if (last_cnt) sc->nnz_active = (int64_t)(c[0] + 0.5);
+}
+
+// ---- K1: CSR SpMV, W lanes per row, fused reductions ---------------------------------------------
+// MODE 0: y = L x
+// MODE 1: Lanczos A-step: x = basis[j] / beta[j]; y = L x; alpha[j] = x.y; ysum[j] = sum y
+// MODE 2: Rayleigh: y = L x; vLv = x.y; vv = x.x
+struct SpmvArgs {
+    int n;
+    int ld;
+    const int* rp;
+    const int* col;
+    const double* val;
+    const double* diag;
+    const double* x;     // MODE 0/2 input; MODE 1: basis base pointer
+    double* y;
+    LzScalars* sc;
+    double* alpha;       // MODE 1
+    const double* beta;  // MODE 1
+    double* ysum;        // MODE 1
+    ReduceWS ws;
+};
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(kBlock) k_spmv(SpmvArgs a) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    const int lane = threadIdx.x & (W - 1);
+    const int sub = (blockIdx.x * kBlock + threadIdx.x) / W;
+    const int nsub = gridDim.x * kBlock / W;
+    constexpr int rows_per_warp = 32 / W;
+    const int sub_in_warp = sub % rows_per_warp;
+
+    const double* __restrict__ x = a.x;
+    double scale = 1.0;
+    int j = 0;
+    if (MODE == 1) {
+        j = a.sc->step;
+        x = a.x + (size_t)j * a.ld;
+        scale = safe_inv(a.beta[j]);
+    }
+    const int* __restrict__ col = a.col;
+    const double* __restrict__ val = a.val;
+
+    double r0 = 0.0, r1 = 0.0;
+    for (int base = sub - sub_in_warp; base < a.n; base += nsub) {
+        const int row = base + sub_in_warp;
+        double acc0 = 0.0, acc1 = 0.0;
+        if (row < a.n) {
+            const int s0 = a.rp[row], s1 = a.rp[row + 1];
+            int s = s0 + lane;
+            for (; s + W < s1; s += 2 * W) {
+                int c0 = ld_stream(col + s), c1 = ld_stream(col + s + W);
+                double v0 = ld_stream(val + s), v1 = ld_stream(val + s + W);
+                acc0 = fma(v0, ld_nc(x + c0), acc0);
+                acc1 = fma(v1, ld_nc(x + c1), acc1);
+            }
+            if (s < s1) acc0 = fma(ld_stream(val + s), ld_nc(x + ld_stream(col + s)), acc0);
+        }
+        acc0 += acc1;
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        if (row < a.n && lane == 0) {
+            const double xi = ld_nc(x + row);
+            const double yi = scale * (a.diag[row] * xi - acc0);
+            a.y[row] = yi;
+            if (MODE == 1) {
+                r0 = fma(xi * scale, yi, r0);
+                r1 += yi;
+            } else if (MODE == 2) {
+                r0 = fma(xi, yi, r0);
+                r1 = fma(xi, xi, r1);
+            }
+        }
+    }
+    if (MODE != 0) {
+        double v[2] = {r0, r1};
+        if (grid_reduce<2>(v, a.ws, sm, &flag)) {
+            if (MODE == 1) {
+                a.alpha[j] = v[0];
+                a.ysum[j] = v[1];
+            } else {
+                a.sc->vLv = v[0];
+                a.sc->vv = v[1];
+            }
+        }
+    }
+}
+
+// ---- K3: Lanczos B-step ---------------------------------------------------------------------------
+// u_{j+1} = y - alpha_j v_j - beta_j v_{j-1} - c 1 ;  beta_{j+1} = ||u_{j+1}|| ; step = j + 1
+// Three-term recurrence of the operator P L P, P = I - 11^T/n: the projection the reference applies
+// to its block at nx:206-210,251 is applied to every Lanczos vector here.  c is the mean of the WHOLE
+// right-hand side -- mean(y) minus the (rounding-level) means the stored u_j, u_{j-1} still carry,
+// which usum[] tracks -- not just mean(y): 0 lies outside the spectrum of P L P on 1-perp, so a
+// 1-component left to the recurrence alone grows like the Lanczos polynomial p_j(0) and the null
+// eigenvalue reappears in T_k after ~100 steps.
+__global__ void __launch_bounds__(kBlock) k_lanczos_b(int n, int ld, double* __restrict__ basis,
+                                                      const double* __restrict__ y, const double* __restrict__ alpha,
+                                                      double* __restrict__ beta, const double* __restrict__ ysum,
+                                                      double* __restrict__ usum, LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    const int j = sc->step;
+    const double a = alpha[j];
+    const double bj = beta[j];
+    const double binv = safe_inv(bj);
+    const double bpinv = (j > 0) ? safe_inv(beta[j - 1]) : 0.0;
+    const double ca = a * binv;        // coefficient of u_j
+    const double cb = bj * bpinv;      // coefficient of u_{j-1}
+    const double c = (ysum[j] - ca * usum[j] - ((j > 0) ? cb * usum[j - 1] : 0.0)) / (double)n;
+    const double* __restrict__ uj = basis + (size_t)j * ld;
+    const double* __restrict__ up = basis + (size_t)(j > 0 ? j - 1 : 0) * ld;
+    double* __restrict__ un = basis + (size_t)(j + 1) * ld;
+    double acc = 0.0, sum = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double w = y[i] - ca * uj[i] - cb * up[i] - c;
+        un[i] = w;
+        acc = fma(w, w, acc);
+        sum += w;
+    }
+    double v[2] = {acc, sum};
+    if (grid_reduce<2>(v, ws, sm, &flag)) {
+        beta[j + 1] = sqrt(v[0]);
+        usum[j + 1] = v[1];
+        sc->step = j + 1;
+    }
+}
+
+// ---- finalisation: Ritz vector, normalisation, residual ------------------------------------------
+// y_raw = sum_t coef[t] basis[t]   (coef[t] = s_t / beta[t] folds the normalisation of u_t)
+__global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const double* __restrict__ basis,
+                                                 const double* __restrict__ coef, double* __restrict__ out,
+                                                 LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    double r0 = 0.0, r1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int t = 0;
+        for (; t + 4 <= k; t += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fma(coef[t + q], basis[(size_t)(t + q) * ld + i], acc[q]);
+        }
+        for (; t < k; ++t) acc[0] = fma(coef[t], basis[(size_t)t * ld + i], acc[0]);
+        double yv = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        out[i] = yv;
+        r0 += yv;
+        r1 = fma(yv, yv, r1);
+    }
+    double v[2] = {r0, r1};
+    if (grid_reduce<2>(v, ws, sm, &flag)) {
+        sc->ritz_sum = v[0];
+        sc->ritz_sq = v[1];
+    }
+}
+
+// v = (y_raw - mean) / ||y_raw - mean||
+__global__ void __launch_bounds__(kBlock) k_center_normalize(int n, double* __restrict__ v, const LzScalars* sc) {
+    const double mean = sc->ritz_sum / (double)n;
+    const double nrm2 = sc->ritz_sq - (double)n * mean * mean;
+    const double inv = (nrm2 > 0.0) ? 1.0 / sqrt(nrm2) : 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = (v[i] - mean) * inv;
+}
+
+// res1 = sum_i | (L v)_i - theta v_i |, theta = vLv / vv   (nx:243)
+__global__ void __launch_bounds__(kBlock) k_resid_l1(int n, const double* __restrict__ v, const double* __restrict__ lv,
+                                                     LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[kWarpsPerBlock];
+    __shared__ int flag;
+    const double theta = sc->vLv / sc->vv;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        acc += fabs(lv[i] - theta * v[i]);
+    double r[1] = {acc};
+    if (grid_reduce<1>(r, ws, sm, &flag)) sc->res1 = r[0];
+}
+
+// ---- K4: gradient g_k = kappa_k (v_i - v_j)^2  (mac.py:117-124), fused ||g||^2 and g.x ------------
+__global__ void __launch_bounds__(kBlock) k_gradient(int64_t m, const int* __restrict__ ci, const int* __restrict__ cj,
+                                                     const double* __restrict__ kappa, const double* __restrict__ v,
+                                                     const double* __restrict__ x, double* __restrict__ g,
+                                                     LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    double r0 = 0.0, r1 = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
+        const double d = ld_nc(v + ld_stream(ci + e)) - ld_nc(v + ld_stream(cj + e));
+        const double kd = __dmul_rn(ld_stream(kappa + e), d);   // kdelta = weight_k * (v_i - v_j)
+        const double ge = __dmul_rn(kd, d);                     // gradf[k] = kdelta * (v_i - v_j)
+        g[e] = ge;
+        r0 = fma(ge, ge, r0);
+        r1 = fma(ge, x[e], r1);
+    }
+    double r[2] = {r0, r1};
+    if (grid_reduce<2>(r, ws, sm, &flag)) {
+        sc->gnorm2 = r[0];
+        sc->gdotx = r[1];
+    }
+}
+
+// ---- K5: top-k by MSD radix select on the order-preserving 64-bit key of g -------------------------
+struct SelState {
+    unsigned long long prefix;   // key bits decided so far
+    unsigned long long mask;     // which bits of `prefix` are decided
+    long long remaining;         // how many of the current bucket still have to be taken
+    long long count_gt;          // elements strictly above the current bucket
+    long long eq_total;          // after the last pass: elements equal to the k-th key
+    unsigned int hist[256];
+};
+
+__device__ __forceinline__ unsigned long long order_key(double g) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(g);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(kBlock) k_sel_init(SelState* st, long long k) {
+    if (threadIdx.x == 0) {
+        st->prefix = 0ull;
+        st->mask = 0ull;
+        st->remaining = k;
+        st->count_gt = 0;
+        st->eq_total = 0;
+    }
+    st->hist[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(kBlock) k_sel_hist(int64_t m, const double* __restrict__ g, SelState* st, int shift) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix, mask = st->mask;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t mceil = ((m + 31) / 32) * 32;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mceil; e += stride) {
+        bool ok = false;
+        unsigned int d = 0xffffffffu;
+        if (e < m) {
+            unsigned long long key = order_key(g[e]);
+            ok = ((key & mask) == prefix);
+            d = ok ? (unsigned int)((key >> shift) & 0xffull) : 0xffffffffu;
+        }
+        // warp-aggregated histogram update (early digits are nearly constant across the array)
+        unsigned int peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[d], (unsigned int)__popc(peers));
+    }
+    __syncthreads();
+    unsigned int c = sh[threadIdx.x];
+    if (c) atomicAdd(&st->hist[threadIdx.x], c);
+}
+
+// One block of 256 threads: walk the histogram from the top digit down to the bucket holding the
+// `remaining`-th largest element; fix that digit.
+__global__ void __launch_bounds__(kBlock) k_sel_pick(SelState* st, int shift) {
+    __shared__ unsigned long long suf[256];
+    const int t = threadIdx.x;
+    const unsigned int h = st->hist[t];
+    suf[t] = h;
+    __syncthreads();
+    // inclusive suffix sum: suf[t] = sum_{d >= t} hist[d]
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned long long add = (t + o < 256) ? suf[t + o] : 0ull;
+        __syncthreads();
+        suf[t] += add;
+        __syncthreads();
+    }
+    const long long rem = st->remaining;
+    const unsigned long long above = suf[t] - h;   // elements in digits > t
+    __syncthreads();
+    if ((long long)above < rem && (long long)suf[t] >= rem) {
+        st->prefix |= ((unsigned long long)t) << shift;
+        st->mask |= 0xffull << shift;
+        st->remaining = rem - (long long)above;
+        st->count_gt += (long long)above;
+        st->eq_total = (long long)h;
+    }
+    st->hist[t] = 0u;
+}
+
+// Selection mask + dual-bound term.  Block b owns the contiguous index range [b*chunk, (b+1)*chunk)
+// so that ties at the k-th key can be ranked by index (lowest index first).
+__global__ void __launch_bounds__(kBlock) k_sel_tie_count(int64_t m, int64_t chunk, const double* __restrict__ g,
+                                                          const SelState* st, unsigned int* __restrict__ blockcnt) {
+    __shared__ unsigned int cnt;
+    if (threadIdx.x == 0) cnt = 0u;
+    __syncthreads();
+    const unsigned long long kth = st->prefix;
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(m, lo + chunk);
+    unsigned int c = 0;
+    for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) c += (order_key(g[e]) == kth) ? 1u : 0u;
+    if (c) atomicAdd(&cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(kBlock) k_sel_tie_scan(int nblocks, unsigned int* __restrict__ blockcnt) {
+    // exclusive scan by one thread: nblocks <= a few thousand, runs only when ties exist
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned int run = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            unsigned int c = blockcnt[b];
+            blockcnt[b] = run;
+            run += c;
+        }
+    }
+}
+
+template <bool RANKED>
+__global__ void __launch_bounds__(kBlock) k_sel_apply(int64_t m, int64_t chunk, const double* __restrict__ g,
+                                                      const double* __restrict__ x, const SelState* st,
+                                                      const unsigned int* __restrict__ blockoff,
+                                                      uint8_t* __restrict__ sel, LzScalars* sc, ReduceWS ws) {
+    __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ int flag;
+    __shared__ unsigned int run;       // ties seen so far in this block's range
+    __shared__ unsigned int wcnt[kWarpsPerBlock];
+    const unsigned long long kth = st->prefix;
+    const long long need = st->remaining;   // ties to take, lowest index first
+    const bool none = (st->mask == 0ull);   // k == 0: nothing selected
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(m, lo + chunk);
+    if (threadIdx.x == 0) run = RANKED ? blockoff[blockIdx.x] : 0u;
+    __syncthreads();
+    double r0 = 0.0, r1 = 0.0;
+    for (int64_t base = lo; base < hi; base += blockDim.x) {
+        const int64_t e = base + threadIdx.x;
+        bool in = e < hi;
+        double ge = in ? g[e] : 0.0;
+        unsigned long long key = in ? order_key(ge) : 0ull;
+        bool take = in && !none && key > kth;
+        bool tie = in && !none && key == kth;
+        if (RANKED) {
+            unsigned int bal = __ballot_sync(0xffffffffu, tie);
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            unsigned int before = run;
+            for (int w = 0; w < warp; ++w) before += wcnt[w];
+            unsigned int rank = before + __popc(bal & ((1u << lane) - 1u));
+            if (tie && (long long)rank < need) take = true;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int tot = 0;
+                for (int w = 0; w < kWarpsPerBlock; ++w) tot += wcnt[w];
+                run += tot;
+            }
+            __syncthreads();
+        } else {
+            take = take || tie;
+        }
+        if (in) {
+            sel[e] = take ? 1 : 0;
+            double sx = (take ? 1.0 : 0.0) - x[e];
+            r0 = fma(ge, sx, r0);
+            r1 += take ? 1.0 : 0.0;
+        }
+    }
+    double r[2] = {r0, r1};
+    if (grid_reduce<2>(r, ws, sm, &flag)) {
+        sc->gs_minus_x = r[0];
+        sc->nsel = (int64_t)(r[1] + 0.5);
+    }
+}
+
+// ---- FW update: x <- x + gamma (s - x)  (frankwolfe.py:76), candidate edge weights refreshed -------
+// The three roundings (s - x, gamma * (.), x + (.)) are kept separate, as numpy evaluates them.
+__global__ void __launch_bounds__(kBlock) k_fw_update(int64_t m, double gamma, const uint8_t* __restrict__ sel,
+                                                      const double* __restrict__ kappa, double tol,
+                                                      double* __restrict__ x, double* __restrict__ ew_cand) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
+        double xe = x[e];
+        double s = sel[e] ? 1.0 : 0.0;
+        double xn = __dadd_rn(xe, __dmul_rn(gamma, __dsub_rn(s, xe)));
+        x[e] = xn;
+        ew_cand[e] = (xn > tol) ? xn * kappa[e] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_mask_to_double(int64_t m, const uint8_t* __restrict__ sel, double* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = sel[e] ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill(int64_t count, double value, double* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = value;
+}
+
+__global__ void k_set_lanczos_start(LzScalars* sc, double* beta, double* usum, double beta0) {
+    sc->step = 0;
+    beta[0] = beta0;
+    usum[0] = 0.0;
+}
+
+}  // namespace macb

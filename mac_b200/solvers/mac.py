@@ -1,0 +1,142 @@
+"""MAC solver: drop-in for `mac.solvers.mac.MAC` (mac/solvers/mac.py:15-225) with the
+Frank-Wolfe loop, the Fiedler eigen-solve, the gradient and the LP step on a B200.
+
+Construction uploads the graph once; `solve` uploads x_init, runs the whole loop on the device
+(`macb_fw_run`) and downloads w.  `problem`, `evaluate_objective` and `laplacian` keep the
+reference's fine-grained seam for user-supplied Frank-Wolfe drivers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from timeit import default_timer as timer
+from typing import Optional
+
+import numpy as np
+
+from .. import _lib
+from ..utils.fiedler import seeded_start, _VALID
+from ..utils.graphs import edges_to_arrays, weight_graph_lap_from_edges, _laplacian
+from ..utils.rounding import round_madow, round_nearest
+
+
+class MAC:
+    @dataclass
+    class Cache:
+        """Problem data cache (mac.py:17-20).  In the reference it is never populated
+        (mac.py:126-127 stores the *input* Q); here `use_cache=True` warm-starts each
+        eigen-solve from the previous Fiedler vector -- same converged pair, fewer steps."""
+        Q: Optional[np.ndarray] = None
+
+    def __init__(self, fixed_edges, candidate_edges, num_nodes, fiedler_method="tracemin_lu", fiedler_tol=1e-8,
+                 min_selection_weight_tol=1e-10, device=-1, fiedler_max_steps=0):
+        """Same parameters as the reference (mac.py:22-44); edges may be lists of `Edge` or
+        (i, j, w) array triples.  `device`, `fiedler_max_steps` are additions."""
+        fi, fj, fw = edges_to_arrays(fixed_edges)
+        ci, cj, ck = edges_to_arrays(candidate_edges)
+        num_edges = len(fi) + len(ci)
+        assert (num_nodes - 1) <= num_edges  # mac.py:47
+        assert num_edges <= 0.5 * num_nodes * (num_nodes - 1)  # mac.py:52
+        if fiedler_method not in _VALID:
+            raise ValueError(f"Unknown linear system solver: {fiedler_method}")
+        self.num_nodes = int(num_nodes)
+        self._fixed = (fi, fj, fw)
+        self._L_fixed = None
+        self.weights = ck
+        self.edge_list = np.stack([ci.astype(np.int64), cj.astype(np.int64)], axis=1) if len(ci) else np.zeros((0, 2), np.int64)
+        self.fiedler_method = fiedler_method
+        self.fiedler_tol = fiedler_tol
+        self.min_selection_weight_tol = min_selection_weight_tol
+        self.fiedler_max_steps = int(fiedler_max_steps)
+        self._h = _lib.Handle(self.num_nodes, fi, fj, fw, ci, cj, ck, device=device)
+        if self.num_nodes >= 2:
+            self._h.set_start(np.ascontiguousarray(seeded_start(self.num_nodes)[:, 0]))  # fiedler.py:27-32
+        self.last_info = {}
+
+    # -- reference attributes
+    @property
+    def L_fixed(self):
+        """scipy CSR of the fixed-edge Laplacian (mac.py:55), built on first access."""
+        if self._L_fixed is None:
+            fi, fj, fw = self._fixed
+            self._L_fixed = _laplacian(fi, fj, fw, self.num_nodes)
+        return self._L_fixed
+
+    def laplacian(self, x):
+        """mac.py:74-89, returned as scipy CSR for compatibility (not used by the device path)."""
+        x = np.asarray(x, dtype=float)
+        idx = np.where(x > self.min_selection_weight_tol)
+        prod = x[idx] * self.weights[idx]
+        return self.L_fixed + weight_graph_lap_from_edges(self.edge_list[idx], prod, self.num_nodes)
+
+    def evaluate_objective(self, x):
+        """mac.py:91-102: lambda2(L(x)), cold solve at `fiedler_tol`."""
+        self._h.set_x(x, self.min_selection_weight_tol)
+        lam, _, info = self._h.fiedler(tol=self.fiedler_tol, max_steps=self.fiedler_max_steps, want_vector=False)
+        self.last_info = info
+        return lam
+
+    def fiedler_pair(self, x, tol=None, warm=False):
+        """(lambda2, v2) of L(x) -- the device counterpart of fiedler.find_fiedler_pair(L(x))."""
+        self._h.set_x(x, self.min_selection_weight_tol)
+        lam, v, info = self._h.fiedler(tol=1e-8 if tol is None else tol, max_steps=self.fiedler_max_steps, warm=warm)
+        self.last_info = info
+        return lam, v
+
+    def problem(self, x, cache=None):
+        """mac.py:104-128: (lambda2(L(x)), supergradient).  As in the reference the FW-side solve
+        always runs at tol 1e-8 (mac.py:115 does not forward fiedler_tol)."""
+        warm = cache is not None and cache.Q is not None
+        self._h.set_x(x, self.min_selection_weight_tol)
+        f, _, info = self._h.fiedler(tol=1e-8, max_steps=self.fiedler_max_steps, warm=warm, want_vector=False)
+        gradf = self._h.gradient()
+        self.last_info = info
+        if cache is not None:
+            cache.Q = True  # the previous vector lives on the device
+        return f, gradf
+
+    def solve_lp(self, k):
+        """The LP oracle on the gradient of the last `problem` call, without a host round trip."""
+        return self._h.topk(k)
+
+    def frank_wolfe(self, k, x_init, max_iters=5, relative_duality_gap_tol=1e-4, grad_norm_tol=1e-8, use_cache=False):
+        """frank_wolfe(initial=x_init, problem=self.problem, solve_lp=top-k) on the device
+        (frankwolfe.py:10-79 as mac.py:196-200 calls it).  Returns (w, u, info)."""
+        w, u, info = self._h.fw_run(k, x_init, max_iters, relative_duality_gap_tol, grad_norm_tol, fiedler_tol=1e-8,
+                                    min_sel_tol=self.min_selection_weight_tol,
+                                    fiedler_max_steps=self.fiedler_max_steps, warm=use_cache)
+        self.last_info = info
+        return w, u, info
+
+    def solve(self, k, x_init=None, rounding="nearest", fallback=False, max_iters=5, relative_duality_gap_tol=1e-4,
+              grad_norm_tol=1e-8, random_rounding_max_iters=1, verbose=False, return_rounding_time=False,
+              use_cache=False):
+        """mac.py:130-225.  Returns (rounded, unrounded, upper_bound[, rounding_time])."""
+        m = len(self.weights)
+        if k >= m:  # mac.py:173-180
+            result = np.ones(m)
+            if return_rounding_time:
+                return result, result, self.evaluate_objective(np.ones(m)), 0.0
+            return result, result, self.evaluate_objective(np.ones(m))
+        assert len(x_init) == m  # mac.py:183
+        x_init = np.asarray(x_init, dtype=float)
+        w, u, info = self.frank_wolfe(k, x_init, max_iters, relative_duality_gap_tol, grad_norm_tol, use_cache)
+        if verbose:
+            for i, (f, ub) in enumerate(zip(info["f_hist"], info["u_hist"])):
+                print(f"iter {i}: f = {f:.12g}, upper = {ub:.12g}")
+        start = timer()
+        if rounding == "madow":
+            rounded = round_madow(w, k, value_fn=self.evaluate_objective, max_iters=random_rounding_max_iters)
+        else:
+            rounded = round_nearest(w, k, weights=self.weights, break_ties_decimal_tol=10)  # mac.py:207
+        rounding_time = timer() - start
+        if fallback:
+            # mac.py:211-218 intends "keep x_init if rounding made things worse" (it raises NameError
+            # in the reference because of a misspelt variable); implemented as intended.
+            if self.evaluate_objective(rounded) < self.evaluate_objective(x_init):
+                rounded = x_init
+        if return_rounding_time:
+            return rounded, w, u, rounding_time
+        return rounded, w, u
+
+    def close(self):
+        self._h.close()
