@@ -391,7 +391,10 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         c->have_v = true;
         return MACB_OK;
     }
-    const double brk = 1e-13 * lnorm;
+    // beta_j below this => span(u_0..u_{j-1}) is invariant to within the requested tolerance: every Ritz
+    // pair of T_j then has residual <= beta_j < tol ||L||_inf / sqrt(n), so T_j is final.  (Dividing by a
+    // beta that small would also amplify rounding noise into the next vector.)
+    const double brk = std::max(1e-12 * lnorm, 0.25 * tol * lnorm / sqrtn);
 
     bool use_warm = warm && c->have_v;
     int total_steps = 0;
@@ -405,9 +408,9 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         c->h_beta[0] = use_warm ? 1.0 : c->x0_norm;
         int k_done = 0;
         double theta_prev = std::numeric_limits<double>::infinity();
-        // no cap at n - 1: without re-orthogonalisation the recurrence simply keeps refining (ghost
-        // copies appear in T_k); a genuinely exhausted Krylov space shows up as beta ~ 0 below.
-        const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)(max_steps - total_steps));
+// at most n - 1 steps per cycle: the Krylov space on 1-perp is exhausted by then, and a cycle
+        // that long without convergence is restarted from its Ritz vector below.
+        const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
         bool invariant = false;
         while (true) {
             int batch;

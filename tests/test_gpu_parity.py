@@ -1,0 +1,404 @@
+"""Parity of the CUDA path (through the C-ABI / Python mirror) against the CPU oracle and the
+reference goldens.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances (stated once):
+  * lambda2: |dev - ref| / ref <= 1e-8 (BASELINE.json asks 1e-6); residual ||Lv - lv||_1/||L||_inf < tol=1e-8,
+    the reference's own stopping test (nx:243), re-evaluated by the oracle on the device's vector.
+  * Fiedler vector / gradient: the reference stops at residual 1e-8, so two converged solvers agree to
+    ~1e-6 of the largest entry, not to machine precision.
+  * LP vertex (top-k): bit-exact for equal inputs; across solvers, equal except for entries whose gradient
+    lies within that eigenvector noise of the k-th largest value.
+  * Frank-Wolfe iterate update: bit-exact for equal selections.
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from mac_b200 import _lib, synth
+from mac_b200.g2o import split_edges
+from mac_b200.optimization.constraints import solve_subset_box_lp
+from mac_b200.optimization.frankwolfe import frank_wolfe
+from mac_b200.solvers import MAC, NaiveGreedy
+from mac_b200.utils.fiedler import find_fiedler_pair
+from mac_b200.utils.graphs import Edge, weight_graph_lap_from_edge_list
+from mac_b200.utils.rounding import round_nearest
+from oracle import mac_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+G_NOISE = 5e-6  # relative (to max g) disagreement two 1e-8-converged eigen-solves may show
+
+
+def _load(golden_dir, name):
+    return json.load(open(os.path.join(golden_dir, name)))
+
+
+def _g2o(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"g2o_{name}.npz"))
+    fixed, cand = split_edges(z["i"], z["j"], z["kappa"])
+    return fixed, cand, int(z["n"])
+
+
+def _same_up_to_sign(a, b):
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+# ------------------------------------------------------------------------------------------- K1 / K2
+@pytest.mark.parametrize("case", ["petersen", "chain300", "er5000", "isolated_candidates"])
+def test_spmv_and_assembly_match_scipy(case):
+    rng = np.random.default_rng(0)
+    if case == "petersen":
+        fixed, cand, n = synth.petersen_split()
+    elif case == "chain300":
+        fixed, cand, n = synth.chain_plus_random(300, 1500, seed=2, weighted=True)
+    elif case == "er5000":
+        fixed, cand, n = synth.chain_plus_random(5000, 60000, seed=1, weighted=True)
+    else:  # ragged: half the nodes have no candidate edge, one duplicate of a fixed edge, one self loop
+        (fi, fj, fw), (ci, cj, ck), n = synth.chain_plus_random(400, 600, seed=4, weighted=True)
+        keep = (ci < 200) & (cj < 200)
+        ci, cj, ck = np.r_[ci[keep], 3, 7].astype(np.int32), np.r_[cj[keep], 4, 7].astype(np.int32), np.r_[ck[keep], 2.5, 9.0]
+        fixed, cand = (fi, fj, fw), (ci, cj, ck)
+    m = len(cand[0])
+    h = _lib.Handle(n, *fixed, *cand)
+    o = orc.OracleMAC(fixed, cand, n)
+    for x in (np.zeros(m), np.ones(m), rng.random(m) * (rng.random(m) > 0.5), np.full(m, 1e-11)):
+        h.set_x(x)
+        L = o.laplacian(x)
+        v = rng.normal(size=n)
+        y = h.spmv(v)
+        ref = L @ v
+        assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        assert abs(h.lnorm() - abs(L).sum(axis=1).max()) <= 1e-12 * max(1.0, h.lnorm())
+        assert np.allclose(h.get_x(), x, rtol=0, atol=0)
+    assert h.sizes()["nnz_union"] == 2 * (np.sum(fixed[0] != fixed[1]) + np.sum(cand[0] != cand[1]))
+    h.close()
+
+
+def test_empty_candidate_set_and_state_errors():
+    fi, fj, fw = synth.complete_graph(5)
+    h = _lib.Handle(5, fi, fj, fw, [], [], [])
+    with pytest.raises(_lib.MacbError):
+        h.fiedler()  # no L(x) yet
+    h.set_x(np.zeros(0))
+    with pytest.raises(_lib.MacbError):
+        h.gradient()  # no Fiedler vector yet
+    lam, v, info = h.fiedler()
+    assert abs(lam - 5.0) < 1e-12 and info["converged"]
+    assert h.gradient().shape == (0,)
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------- K3
+def test_k5_known_answer_through_find_fiedler_pair():
+    # reference tests/utils/test_fiedler.py:26-33
+    edges = [Edge(i, j, 1.0) for i in range(5) for j in range(i + 1, 5)]
+    L = weight_graph_lap_from_edge_list(edges, 5)
+    lam, vec, X = find_fiedler_pair(L)
+    assert np.isclose(lam, 5)
+    assert X.shape == (5, 4) and abs(np.linalg.norm(vec) - 1) < 1e-12 and abs(vec.sum()) < 1e-12
+    with pytest.raises(ValueError):
+        find_fiedler_pair(L, method="bogus")
+
+
+@pytest.mark.parametrize("name,k", [("intel", 157), ("intel", 78), ("sphere2500", 1225), ("city10000", 1068)])
+def test_fiedler_pair_matches_reference_on_g2o(golden_dir, name, k):
+    fixed, cand, n = _g2o(golden_dir, name)
+    W = np.load(os.path.join(golden_dir, "g2o_fw_w.npz"))
+    gold = _load(golden_dir, "g2o_fw.json")[name]["runs"][str(k)]
+    x0 = W[f"{name}_{k}_xinit"]
+    mac = MAC(fixed, cand, n)
+    lam, v = mac.fiedler_pair(x0)
+    assert mac.last_info["converged"]
+    assert abs(lam - gold["naive_l2"]) / gold["naive_l2"] <= 1e-8
+    assert abs(np.linalg.norm(v) - 1) < 1e-12 and abs(v.sum()) < 1e-10
+    L = orc.OracleMAC(fixed, cand, n).laplacian(x0)
+    assert orc.residual_l1(L, lam, v) < 1e-8
+    assert _same_up_to_sign(v, W[f"{name}_{k}_v0"]) < 5e-6
+    assert abs(mac.evaluate_objective(x0) - lam) <= 1e-12
+    mac.close()
+
+
+def test_fiedler_small_and_awkward_graphs():
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(2, 70))
+        ei = np.arange(1, n)
+        ej = np.array([int(rng.integers(0, i)) for i in range(1, n)])
+        extra = rng.integers(0, n, size=(int(rng.integers(0, 3 * n)), 2))
+        extra = extra[extra[:, 0] != extra[:, 1]]
+        ei, ej = np.r_[ei, extra[:, 0]], np.r_[ej, extra[:, 1]]
+        w = rng.uniform(0.1, 10, len(ei)) if trial % 2 else np.ones(len(ei))
+        h = _lib.Handle(n, ei, ej, w, [], [], [])
+        h.set_x(np.zeros(0))
+        lam, v, info = h.fiedler()
+        ev = np.linalg.eigvalsh(orc.laplacian_from_edges(n, ei, ej, w).toarray())
+        assert info["converged"], (trial, n, info)
+        assert abs(lam - ev[1]) <= 1e-8 * max(1.0, ev[1]), (trial, n, lam, ev[:3])
+        h.close()
+
+
+def test_disconnected_graph_has_zero_connectivity():
+    # the reference skips this case (tests/utils/test_fiedler.py:43-50); the device solver returns ~0
+    ei = np.array([0, 0, 1, 3, 3, 4])
+    ej = np.array([1, 2, 2, 4, 5, 5])
+    h = _lib.Handle(6, ei, ej, np.ones(6), [], [], [])
+    h.set_x(np.zeros(0))
+    lam, v, info = h.fiedler()
+    assert abs(lam) < 1e-9
+    h.close()
+
+
+def test_warm_start_reaches_the_same_pair():
+    fixed, cand, n = synth.chain_plus_random(3000, 30000, seed=5, weighted=True)
+    mac = MAC(fixed, cand, n)
+    x = synth.first_k_init(30000, 6000)
+    lam0, v0 = mac.fiedler_pair(x)
+    x2 = x.copy()
+    x2[6000:6100] = 0.5
+    lam_cold, v_cold = mac.fiedler_pair(x2)
+    mac.fiedler_pair(x)
+    lam_warm, v_warm = mac.fiedler_pair(x2, warm=True)
+    assert abs(lam_cold - lam_warm) <= 1e-9 * lam_cold
+    assert _same_up_to_sign(v_cold, v_warm) < 5e-6
+    mac.close()
+
+
+# ------------------------------------------------------------------------------------------- K4
+def test_gradient_matches_oracle(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "er2000.npz"))
+    fixed, cand, n = synth.chain_plus_random(2000, 20000, seed=0, weighted=True)
+    mac = MAC(fixed, cand, n)
+    o = orc.OracleMAC(fixed, cand, n)
+    x = synth.first_k_init(20000, 4000)
+    f, g = mac.problem(x)
+    assert abs(f - _load(golden_dir, "er2000.json")["lambda2_init"]) <= 1e-9
+    assert np.abs(g - gold["g0"]).max() <= G_NOISE * gold["g0"].max()     # vs the reference's gradient
+    lam, v = mac.fiedler_pair(x)
+    g_dev = mac._h.gradient()
+    assert np.array_equal(g_dev, o.gradient(v))                             # same v => bit-exact (mac.py:117-124)
+    mac.close()
+
+
+# ------------------------------------------------------------------------------------------- K5
+def test_topk_bit_exact_and_tie_rules():
+    rng = np.random.default_rng(3)
+    for m, k in [(1, 1), (7, 3), (1000, 1), (1000, 999), (50000, 12345), (300001, 60000)]:
+        g = rng.random(m) ** 3
+        s = solve_subset_box_lp(g, k)
+        ref = np.zeros(m)
+        ref[np.argsort(-g, kind="stable")[:k]] = 1.0
+        assert np.array_equal(s, ref)
+    g = rng.normal(size=4097)  # negative values and zeros order correctly
+    g[::7] = 0.0
+    g[5] = -0.0
+    s = solve_subset_box_lp(g, 2000)
+    thr = np.sort(g)[-2000]
+    assert s.sum() == 2000 and (s[g > thr] == 1).all() and (s[g < thr] == 0).all()
+    # exact ties: lowest index first
+    g = np.ones(5000)
+    s = solve_subset_box_lp(g, 1234)
+    assert s[:1234].all() and not s[1234:].any()
+    g = np.r_[np.full(3000, 2.0), np.full(3000, 5.0), np.full(3000, 2.0)]
+    s = solve_subset_box_lp(g, 3500)
+    assert s[3000:6000].all() and s[:500].all() and s.sum() == 3500
+    assert solve_subset_box_lp(g, 0).sum() == 0 and round_nearest(g, len(g)).sum() == len(g)
+    # reference tests/optimization/test_frankwolfe.py:36-51
+    problem = lambda x: (-np.inner(x, x), -2 * x)  # noqa: E731
+    init = np.array([0.3, 0.7])
+    x, u = frank_wolfe(init, problem, lambda gg: solve_subset_box_lp(gg, 1))
+    assert np.allclose(x, [0.5, 0.5], atol=0.01)
+
+
+# ------------------------------------------------------------------------------------------- FW loop
+def _teacher_forced(mac, o, k, x, iters):
+    """Feed the same iterate to device and oracle; compare f, g and the LP vertex per iteration."""
+    for i in range(iters):
+        f, g = mac.problem(x)
+        fo, go = o.problem(x)
+        assert abs(f - fo) <= 1e-8 * abs(fo), (i, f, fo)
+        noise = G_NOISE * go.max()
+        assert np.abs(g - go).max() <= noise, (i, np.abs(g - go).max(), go.max())
+        s = mac.solve_lp(k)
+        so = orc.solve_subset_box_lp(go, k)
+        assert s.sum() == k
+        assert np.array_equal(s, solve_subset_box_lp(g, k))          # device LP on device g == stateless LP
+        kth = np.sort(go)[-k]
+        diff = np.flatnonzero(s != so)
+        assert (np.abs(go[diff] - kth) <= 2 * noise).all(), (i, len(diff))
+        x = x + 2.0 / (i + 2.0) * (so - x)                              # follow the oracle's trajectory
+
+
+def test_fw_teacher_forced_er2000():
+    fixed, cand, n = synth.chain_plus_random(2000, 20000, seed=0, weighted=True)
+    _teacher_forced(MAC(fixed, cand, n), orc.OracleMAC(fixed, cand, n), 4000, synth.first_k_init(20000, 4000), 4)
+
+
+def test_fw_teacher_forced_intel(golden_dir):
+    fixed, cand, n = _g2o(golden_dir, "intel")
+    x0 = NaiveGreedy(cand[2]).subset(157)
+    _teacher_forced(MAC(fixed, cand, n), orc.OracleMAC(fixed, cand, n), 157, x0, 5)
+
+
+def test_fused_loop_equals_composed_loop():
+    """macb_fw_run == the same kernels driven one call at a time through the fine seam."""
+    fixed, cand, n = synth.chain_plus_random(1500, 12000, seed=9, weighted=True)
+    mac = MAC(fixed, cand, n)
+    k = 2400
+    x0 = synth.first_k_init(12000, k)
+    w, u, info = mac.frank_wolfe(k, x0, 6, 0.0, 0.0)
+    x, ub = x0, np.inf
+    fs = []
+    for i in range(6):
+        f, g = mac.problem(x)
+        s = mac.solve_lp(k)
+        ub = min(ub, f + g @ (s - x))
+        fs.append(f)
+        x = x + 2.0 / (i + 2.0) * (s - x)
+    assert np.array_equal(w, x)
+    assert np.allclose(info["f_hist"], fs, rtol=1e-13)
+    assert abs(u - ub) <= 1e-11 * abs(ub)
+    mac.close()
+
+
+@pytest.mark.parametrize("k", [0, 3])
+def test_petersen_matches_reference_bitwise_where_unambiguous(golden_dir, k):
+    # K = 0 and K = 3 (BASELINE config 1) have no LP ties along the trajectory; K = 1, 2, 4, 5 hit
+    # exact ties of the symmetric graph (SURVEY hard part 3) and are covered by the property test below.
+    gold = _load(golden_dir, "petersen.json")["runs"][str(k)]
+    fixed, cand, n = synth.petersen_split()
+    mac = MAC(fixed, cand, n)
+    rounded, w, u = mac.solve(k, synth.first_k_init(6, k), max_iters=100)
+    assert mac.last_info["iters"] == len(gold["hist"])
+    assert np.allclose(mac.last_info["f_hist"], [h["f"] for h in gold["hist"]], rtol=1e-8)
+    assert np.allclose(w, gold["w"], rtol=0, atol=1e-12)
+    assert abs(u - gold["u"]) <= 1e-7
+    assert np.array_equal(rounded, np.array(gold["rounded"]))
+    _, w1, u1 = mac.solve(k, synth.first_k_init(6, k), max_iters=1)
+    assert np.array_equal(w1, np.array(gold["w_after_1"])) and abs(u1 - gold["u_after_1"]) <= 1e-7
+    mac.close()
+
+
+def test_petersen_regression_property_all_budgets(golden_dir):
+    # reference tests/solvers/test_mac.py:35-61: lambda2(unrounded) >= lambda2(x_init) for every budget
+    gold = _load(golden_dir, "petersen.json")["runs"]
+    fixed, cand, n = synth.petersen_split()
+    for pct in [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]:
+        k = int(pct * 6)
+        x_init = synth.first_k_init(6, k)
+        mac = MAC(fixed, cand, n)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            result, unrounded, upper = mac.solve(k, x_init, max_iters=100)
+        init_l2 = mac.evaluate_objective(x_init)
+        assert abs(init_l2 - gold[str(k)]["init_l2"]) <= 1e-9
+        assert mac.evaluate_objective(unrounded) >= init_l2 - 1e-12
+        assert result.sum() == k and set(np.unique(result)) <= {0.0, 1.0}
+        assert upper >= mac.evaluate_objective(unrounded) - 1e-9     # dual bound is an upper bound
+        mac.close()
+
+
+@pytest.mark.parametrize("name,k", [("intel", 157), ("intel", 706), ("sphere2500", 2205), ("city10000", 9619)])
+def test_g2o_protocol_end_to_end(golden_dir, name, k):
+    """g2o_experiment.py:306-321.  The chosen budgets keep every LP step's k-th/(k+1)-th gap above the
+    eigenvector noise (see the gaps recorded in g2o_fw.json), so the whole trajectory must match."""
+    fixed, cand, n = _g2o(golden_dir, name)
+    W = np.load(os.path.join(golden_dir, "g2o_fw_w.npz"))
+    gold = _load(golden_dir, "g2o_fw.json")[name]["runs"][str(k)]
+    mac = MAC(fixed, cand, n)
+    x_init = NaiveGreedy(cand[2]).subset(k)
+    assert np.array_equal(x_init, W[f"{name}_{k}_xinit"])
+    rounded, w, u, t_round = mac.solve(k, x_init, max_iters=20, rounding="nearest", return_rounding_time=True, use_cache=False)
+    assert mac.last_info["iters"] == gold["iters"]
+    assert np.allclose(mac.last_info["f_hist"], [h["f"] for h in gold["hist"]], rtol=1e-7)
+    assert np.abs(w - W[f"{name}_{k}_w"]).max() <= 1e-12
+    assert np.array_equal(rounded, W[f"{name}_{k}_rounded"])
+    assert abs(u - gold["u"]) <= 1e-6 * abs(gold["u"])
+    assert abs(mac.evaluate_objective(w) - gold["unrounded_l2"]) <= 1e-8 * gold["unrounded_l2"]
+    assert abs(mac.evaluate_objective(rounded) - gold["rounded_l2"]) <= 1e-8 * gold["rounded_l2"]
+    assert t_round >= 0.0
+    mac.close()
+
+
+def test_g2o_protocol_quality_when_trajectory_is_tie_sensitive(golden_dir):
+    # city10000 K=1068: all kappa = 100, k-th gap 3e-6 at iteration 12 => the vertex sequence may differ;
+    # the relaxation value and the dual bound must still agree closely.
+    fixed, cand, n = _g2o(golden_dir, "city10000")
+    gold = _load(golden_dir, "g2o_fw.json")["city10000"]["runs"]["1068"]
+    mac = MAC(fixed, cand, n)
+    x_init = NaiveGreedy(cand[2]).subset(1068)
+    rounded, w, u = mac.solve(1068, x_init, max_iters=20)
+    lam = mac.evaluate_objective(w)
+    assert abs(lam - gold["unrounded_l2"]) <= 2e-2 * gold["unrounded_l2"]
+    assert abs(u - gold["u"]) <= 2e-2 * gold["u"]
+    assert rounded.sum() == 1068 and lam <= u * (1 + 1e-9)
+    mac.close()
+
+
+def test_solve_api_surface():
+    fixed, cand, n = synth.chain_plus_random(200, 900, seed=2, weighted=True)
+    mac = MAC(fixed, cand, n)
+    m = 900
+    r, w, u = mac.solve(m, np.ones(m))                      # k >= m shortcut (mac.py:173-180)
+    assert r.sum() == m and np.array_equal(r, w) and abs(u - mac.evaluate_objective(np.ones(m))) < 1e-12
+    out = mac.solve(m + 5, np.ones(m), return_rounding_time=True)
+    assert len(out) == 4 and out[3] == 0.0
+    with pytest.raises(AssertionError):
+        mac.solve(10, np.ones(m - 1))                       # mac.py:183
+    x0 = synth.first_k_init(m, 180)
+    r, w, u = mac.solve(180, x0, max_iters=8, rounding="madow")
+    assert r.sum() == 180
+    r2, w2, u2 = mac.solve(180, x0, max_iters=8, use_cache=True)       # warm-started eigen-solves
+    assert np.abs(w2 - w).max() <= 1e-12 and abs(u2 - u) <= 1e-7 * abs(u)
+    r3, _, _ = mac.solve(180, x0, max_iters=8, fallback=True)
+    assert r3.sum() == 180
+    L = mac.laplacian(x0)
+    assert abs(L - orc.OracleMAC(fixed, cand, n).laplacian(x0)).max() == 0
+    assert mac.weights.shape == (m,) and mac.edge_list.shape == (m, 2) and mac.L_fixed.shape == (n, n)
+    # user-supplied Frank-Wolfe driver over the fine seam (frankwolfe.py:10-17)
+    xf, uf = frank_wolfe(x0, mac.problem, lambda g: solve_subset_box_lp(g, 180), maxiter=8,
+                         relative_duality_gap_tol=1e-4, grad_norm_tol=1e-8)
+    assert np.abs(xf - w).max() <= 1e-12
+    mac.close()
+
+
+def test_early_exit_matches_reference_iteration_count(golden_dir):
+    # intel K=706 stops after 3 iterations on the duality-gap test (frankwolfe.py:71-74)
+    fixed, cand, n = _g2o(golden_dir, "intel")
+    mac = MAC(fixed, cand, n)
+    mac.solve(706, NaiveGreedy(cand[2]).subset(706), max_iters=20)
+    assert mac.last_info["iters"] == 3
+    mac.close()
+
+
+# ------------------------------------------------------------------------------------------- headline size
+def test_headline_size_properties():
+    """BASELINE config 5 at full size (n = 100k, m = 1M, K = 200k): size-independent properties."""
+    fixed, cand, n, k, x0 = synth.headline()
+    mac = MAC(fixed, cand, n)
+    h = mac._h
+    lam, v = mac.fiedler_pair(x0)
+    assert mac.last_info["converged"]
+    Lv = h.spmv(v)                                           # independent residual through the SpMV entry point
+    assert np.abs(Lv - lam * v).sum() / h.lnorm() < 1e-8
+    assert abs(np.linalg.norm(v) - 1) < 1e-12 and abs(v.sum()) < 1e-9
+    assert abs(v @ Lv - lam) <= 1e-12 * lam
+    # linearity of the SpMV
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=n), rng.normal(size=n)
+    assert np.abs(h.spmv(2 * a - 3 * b) - (2 * h.spmv(a) - 3 * h.spmv(b))).max() < 1e-11
+    assert np.abs(h.spmv(np.ones(n))).max() < 1e-12          # L 1 = 0
+    g = h.gradient()
+    d = v[cand[0]] - v[cand[1]]
+    assert np.array_equal(g, (cand[2] * d) * d)
+    s = h.topk(k)
+    assert s.sum() == k and g[s == 1].min() >= g[s == 0].max()
+    w, u, info = mac.frank_wolfe(k, x0, 3, 0.0, 0.0)
+    assert info["iters"] == 3 and abs(info["f_hist"][0] - lam) <= 1e-12
+    assert w.min() >= 0 and w.max() <= 1 and w.sum() <= k * (1 + 1e-12)
+    assert u >= info["f_hist"].max() - 1e-9
+    c = h.counters()
+    assert c["kernel_launches"] > 0 and c["spmv_launches"] > 0
+    mac.close()
