@@ -1,0 +1,278 @@
+"""Headline benchmark: Frank-Wolfe iterations/sec (= Fiedler solves/sec) on BASELINE.json configs[4]
+(chain + random graph, n = 100 000, 1 000 000 candidate edges, K = 200 000), one graph per GPU.
+
+    python bench.py --gpus 1 --steps 50 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
+
+A "step" is one Frank-Wolfe iteration: assemble L(x) -> Fiedler pair -> gradient -> top-K LP -> dual bound,
+stop tests -> x update.  Early exit is disabled (both tolerances 0) so exactly K steps run.
+
+Timing: `value` = N*K / (max over ranks of the summed per-iteration CUDA-event times); every iteration is
+bracketed by its own event pair on the library's stream and a 512 MB buffer (> 126 MB L2) is rewritten between
+iterations outside the brackets.  `e2e` = the same K iterations through the public `MAC.frank_wolfe` call with
+host numpy buffers (x_init uploaded, w / u / histories downloaded inside the timed region), wall clock, no
+bench hooks.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fw_iters_per_sec"
+UNIT = "it/s"
+N_NODES, N_CAND, BUDGET_FRAC = 100_000, 1_000_000, 0.2
+WORKLOAD = "chain+random graph n=100000, 1000000 candidate edges, K=200000, x_init=first-K (BASELINE configs[4])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_problem(seed):
+    from mac_b200 import synth
+    return synth.headline(seed=seed, n=N_NODES, m=N_CAND)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_fw(fixed, cand, n, k, x0, budget_s, max_steps):
+    """The reference's algorithm on the host (oracle port; eigen-solve = the scipy/ARPACK path BASELINE.md
+    section 3 names, since sparse LU does not finish at this size).  Runs whole FW iterations until
+    `budget_s` seconds or `max_steps`; returns (iterations, seconds)."""
+    from oracle import mac_oracle as orc
+    mac = orc.OracleMAC(fixed, cand, n, fw_fiedler_method="arpack")
+    x, u, done = x0, float("inf"), 0
+    t0 = time.perf_counter()
+    while done < max_steps:
+        f, g = mac.problem(x)
+        s = orc.solve_subset_box_lp(g, k)
+        u = min(u, f + g @ (s - x))
+        x = x + orc.naive_stepsize(done) * (s - x)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def threads_used():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fixed, cand, n, k, x0 = make_problem(0)
+    if args.warmup > 0:
+        cpu_fw(fixed, cand, n, k, x0, 0.0, 1)  # one untimed iteration: imports, page-in
+    iters, secs = cpu_fw(fixed, cand, n, k, x0, args.cpu_budget, args.steps)
+    value = iters / secs
+    sample = f"{iters} whole FW iterations of the same workload (time-boxed to {args.cpu_budget:.0f} s of the requested {args.steps})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cpu_path": "oracle port of MAC.solve's loop, eigen-solve = scipy ARPACK eigsh(which='SM') "
+                   "(networkx 'lanczos'); the reference's default sparse-LU TraceMIN does not finish one solve at this size "
+                   "(BASELINE.md: > 3000 s)", "steps_measured": iters},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads_used(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, local_rank, world):
+    from mac_b200.solvers import MAC
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(vals):
+        if dist is None:
+            return list(vals)
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    fixed, cand, n, k, x0 = make_problem(rank)  # one graph per GPU (seed = rank), fixed per-GPU work
+    mac = MAC(fixed, cand, n, device=local_rank)
+    h = mac._h
+    K, W = args.steps, max(args.warmup, 0)
+
+    if W > 0:
+        mac.frank_wolfe(k, x0, W, 0.0, 0.0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-timed region: per-iteration CUDA events, L2 flushed between iterations
+    h.set_bench(True, True)
+    h.reset_counters()
+    h.device_sync(); barrier()
+    t0 = time.perf_counter()
+    w, u, info = mac.frank_wolfe(k, x0, K, 0.0, 0.0)
+    h.device_sync(); barrier()
+    wall_timed = time.perf_counter() - t0
+    iter_ms = h.iter_ms()
+    dev_s = float(iter_ms.sum()) / 1e3
+    counters = h.counters()
+    assert info["iters"] == K and len(iter_ms) == K
+
+    # ---- end-to-end region: the public call, host buffers, no bench hooks
+    h.set_bench(False, False)
+    h.device_sync(); barrier()
+    t0 = time.perf_counter()
+    w2, u2, info2 = mac.frank_wolfe(k, x0, K, 0.0, 0.0)
+    h.device_sync(); barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.array_equal(w, w2)
+
+    dev_max, e2e_max = max_over_ranks([dev_s, e2e_s])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CSR SpMV): back-to-back launches on the library stream, CUDA events
+    peak, peak_kind = peaks()
+    h.set_x(w)
+    spmv_ms, algo_bytes = h.spmv_bench(300, False)
+    spmv_cold_ms, _ = h.spmv_bench(30, True)
+    sizes = h.sizes()
+    achieved = algo_bytes / (spmv_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+
+    line = {
+        "metric": METRIC, "value": world * K / dev_max, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_max * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD, "parallelism": f"one graph per GPU x{world} (seed = rank), no data-path collective",
+            "l2": "512 MB buffer rewritten between timed iterations (outside the event brackets); each iteration also "
+                  "writes its own Lanczos basis (> L2)",
+            "timing": "sum of per-iteration CUDA-event brackets on the library stream, max over ranks",
+            "lanczos_steps_per_solve": counters["lanczos_steps"] / max(counters["fiedler_solves"], 1),
+            "nnz_union": sizes["nnz_union"], "nnz_active_final": sizes["nnz_active"],
+            "wall_s_timed_region_incl_flush": wall_timed, "final_lambda2": float(info["f_hist"][-1]), "dual_bound": u,
+            "spmv_us_l2_resident": spmv_ms * 1e3, "spmv_us_l2_flushed": spmv_cold_ms * 1e3,
+            "roofline_peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        },
+        "e2e": {"value": world * K / e2e_max, "unit": UNIT,
+                "h2d_bytes_per_step": 8 * len(x0) / K, "d2h_bytes_per_step": (8 * len(x0) + 16 * K + 16) / K,
+                "api": "MAC.frank_wolfe(k, x_init, max_iters=K) -> macb_fw_run, host numpy buffers"},
+        "gpu_launches": counters["kernel_launches"],
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv (CSR SpMV, L(w) v)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "note": "algorithmic bytes / CUDA-event time, matrix L2-resident as inside a solve; "
+                             "L2-flushed figure in config.spmv_us_l2_flushed"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fixed0, cand0, n0, k0, x00 = (fixed, cand, n, k, x0)
+        iters, secs = cpu_fw(fixed0, cand0, n0, k0, x00, args.cpu_baseline_budget, 3)
+        line["cpu_baseline"] = {"value": iters / secs, "unit": UNIT, "cores": threads_used(), "kind": "port",
+                                "sample": f"{iters} whole FW iterations of the same workload (oracle, scipy ARPACK eigen-solve)"}
+    print(json.dumps(line), flush=True)
+    mac.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--cpu-baseline-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,16 @@ int macb_sizes(macb_handle h, int64_t* n, int64_t* m, int64_t* nnz_union, int64_
 /* Writes a buffer larger than L2 (bench hygiene between timed steps). */
 int macb_l2_flush(macb_handle h);
 
+/* Bench mode for macb_fw_run: every FW iteration is bracketed by its own pair of CUDA events on the
+ * handle's stream, and -- if flush_l2_between_iters != 0 -- a buffer larger than L2 is rewritten
+ * between iterations, outside those brackets.  macb_iter_ms returns the per-iteration device
+ * milliseconds of the last macb_fw_run (up to cap entries; *count = iterations recorded). */
+int macb_set_bench(macb_handle h, int time_iters, int flush_l2_between_iters);
+int macb_iter_ms(macb_handle h, double* ms, int cap, int* count);
+
+/* cudaDeviceSynchronize on the handle's device. */
+int macb_device_sync(macb_handle h);
+
 /* ---- host-only helpers (no GPU needed; exported for the CPU test-suite) ----------------------- */
 
 /* Smallest eigenpair of the symmetric tridiagonal T_k (diagonal a[0..k), off-diagonal b[1..k)):

@@ -69,6 +69,9 @@ def lib():
     _sig(L.macb_spmv_bench, [H, C.c_int, C.c_int, _dp, _dp])
     _sig(L.macb_sizes, [H, _lp, _lp, _lp, _lp])
     _sig(L.macb_l2_flush, [H])
+    _sig(L.macb_set_bench, [H, C.c_int, C.c_int])
+    _sig(L.macb_iter_ms, [H, _dp, C.c_int, C.POINTER(C.c_int)])
+    _sig(L.macb_device_sync, [H])
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_version, [], C.c_char_p)
@@ -220,6 +223,19 @@ class Handle:
 
     def l2_flush(self):
         self._check(self._L.macb_l2_flush(self._h), "macb_l2_flush")
+
+    def set_bench(self, time_iters=True, flush_l2_between_iters=True):
+        self._L.macb_set_bench(self._h, int(bool(time_iters)), int(bool(flush_l2_between_iters)))
+
+    def iter_ms(self):
+        cnt = C.c_int()
+        self._L.macb_iter_ms(self._h, None, 0, C.byref(cnt))
+        ms = np.zeros(max(cnt.value, 1))
+        self._L.macb_iter_ms(self._h, _p(ms, _dp), cnt.value, C.byref(cnt))
+        return ms[:cnt.value]
+
+    def device_sync(self):
+        self._check(self._L.macb_device_sync(self._h), "macb_device_sync")
 
 
 def topk_dense(g, k, device=-1):

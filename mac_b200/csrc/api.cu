@@ -101,6 +101,9 @@ struct macb_ctx {
     double phase_ms[MACB_T_COUNT] = {0, 0, 0, 0, 0, 0};
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool bench_time_iters = false, bench_flush = false;
+    cudaEvent_t it0 = nullptr, it1 = nullptr;
+    std::vector<double> iter_ms;
 
     std::string err;
 
@@ -223,6 +226,8 @@ void free_all(macb_ctx* c) {
     if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->it0) cudaEventDestroy(c->it0);
+    if (c->it1) cudaEventDestroy(c->it1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -596,6 +601,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
+        CK(cudaEventCreate(&c->it0));
+        CK(cudaEventCreate(&c->it1));
         c->n = n;
         c->ld = ((n + 31) / 32) * 32;
         c->nf = nf;
@@ -812,7 +819,23 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
         double u = std::numeric_limits<double>::infinity();
         int status = MACB_OK;
         int it = 0;
+        h->iter_ms.clear();
+        auto close_iter = [&]() {
+            if (!h->bench_time_iters) return;
+            CK(cudaEventRecord(h->it1, h->stream));
+            CK(cudaEventSynchronize(h->it1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->it0, h->it1));
+            h->iter_ms.push_back(ms);
+        };
         for (; it < max_iters; ++it) {
+            if (h->bench_time_iters) {
+                if (h->bench_flush) {
+                    if (!h->d_flush) CK(cudaMalloc(&h->d_flush, kFlushBytes));
+                    CK(cudaMemsetAsync(h->d_flush, it & 0xff, kFlushBytes, h->stream));
+                }
+                CK(cudaEventRecord(h->it0, h->stream));
+            }
             launch_assemble(h);  // L(x)                          mac.py:115 -> :74
             h->have_x = true;
             FiedlerResult fr;    // f, v                          mac.py:115 -> fiedler.py:9
@@ -827,10 +850,12 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
             if (f_hist) f_hist[it] = f;
             if (u_hist) u_hist[it] = u;
             if (std::sqrt(h->h_sc->gnorm2) < grad_norm_tol) {  // frankwolfe.py:65
+                close_iter();
                 ++it;
                 break;
             }
             if ((u - f) < rel_gap_tol * std::fabs(f)) {  //       frankwolfe.py:71
+                close_iter();
                 ++it;
                 break;
             }
@@ -844,6 +869,7 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
                     h->c_launches++;
                 }
             }
+            close_iter();
         }
         // the loop leaves L(x) stale with respect to d_x if it ran to max_iters; mark state accordingly
         h->have_x = false;
@@ -900,6 +926,29 @@ int macb_l2_flush(macb_handle h) {
         if (!h->d_flush) CK(cudaMalloc(&h->d_flush, kFlushBytes));
         CK(cudaMemsetAsync(h->d_flush, 0xA5, kFlushBytes, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        return (int)MACB_OK;
+    });
+}
+
+int macb_set_bench(macb_handle h, int time_iters, int flush_l2_between_iters) {
+    if (!h) return MACB_ERR_ARG;
+    h->bench_time_iters = time_iters != 0;
+    h->bench_flush = flush_l2_between_iters != 0;
+    return MACB_OK;
+}
+
+int macb_iter_ms(macb_handle h, double* ms, int cap, int* count) {
+    if (!h) return MACB_ERR_ARG;
+    int nrec = (int)h->iter_ms.size();
+    if (count) *count = nrec;
+    if (ms)
+        for (int i = 0; i < std::min(cap, nrec); ++i) ms[i] = h->iter_ms[i];
+    return MACB_OK;
+}
+
+int macb_device_sync(macb_handle h) {
+    return guarded(h, [&]() {
+        CK(cudaDeviceSynchronize());
         return (int)MACB_OK;
     });
 }

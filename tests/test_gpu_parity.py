@@ -29,7 +29,8 @@ from oracle import mac_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-G_NOISE = 5e-6  # relative (to max g) disagreement two 1e-8-converged eigen-solves may show
+G_NOISE = 5e-6  # relative (to max g) disagreement two 1e-8-converged eigen-solves show on well-separated spectra
+G_NOISE_POSE = 2e-4  # pose graphs: lambda3 - lambda2 ~ 1e-2 against ||L|| ~ 3e3, so residual 1e-8 pins v far less tightly
 
 
 def _load(golden_dir, name):
@@ -213,13 +214,13 @@ def test_topk_bit_exact_and_tie_rules():
 
 
 # ------------------------------------------------------------------------------------------- FW loop
-def _teacher_forced(mac, o, k, x, iters):
+def _teacher_forced(mac, o, k, x, iters, g_noise=G_NOISE):
     """Feed the same iterate to device and oracle; compare f, g and the LP vertex per iteration."""
     for i in range(iters):
         f, g = mac.problem(x)
         fo, go = o.problem(x)
         assert abs(f - fo) <= 1e-8 * abs(fo), (i, f, fo)
-        noise = G_NOISE * go.max()
+        noise = g_noise * go.max()
         assert np.abs(g - go).max() <= noise, (i, np.abs(g - go).max(), go.max())
         s = mac.solve_lp(k)
         so = orc.solve_subset_box_lp(go, k)
@@ -239,7 +240,7 @@ def test_fw_teacher_forced_er2000():
 def test_fw_teacher_forced_intel(golden_dir):
     fixed, cand, n = _g2o(golden_dir, "intel")
     x0 = NaiveGreedy(cand[2]).subset(157)
-    _teacher_forced(MAC(fixed, cand, n), orc.OracleMAC(fixed, cand, n), 157, x0, 5)
+    _teacher_forced(MAC(fixed, cand, n), orc.OracleMAC(fixed, cand, n), 157, x0, 5, g_noise=G_NOISE_POSE)
 
 
 def test_fused_loop_equals_composed_loop():
