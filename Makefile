@@ -17,3 +17,7 @@ ptxas-info:
 clean:
 	rm -f $(OUT)
 .PHONY: all clean ptxas-info
+
+# debug variant with per-phase clock64 stamps inside the persistent Lanczos kernel (tools/ptiming.py)
+timing: $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -DMACB_PTIMING -shared -o mac_b200/libmacb200_timing.so $(SRC)

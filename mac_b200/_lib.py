@@ -11,7 +11,7 @@ import warnings
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmacb200.so")
+LIB_PATH = os.environ.get("MACB_LIB", os.path.join(_HERE, "libmacb200.so"))
 
 MACB_OK = 0
 MACB_NOT_CONVERGED = 1

@@ -81,6 +81,15 @@ struct macb_ctx {
     double *h_alpha = nullptr, *h_beta = nullptr;  // pinned
     LzScalars* h_sc = nullptr;                     // pinned
     cudaGraphExec_t lz_graph = nullptr;
+    // persistent engine
+    bool persist = true;
+    int p_ncta = 1;
+    int* d_row_start = nullptr;
+    double* d_sect[2] = {nullptr, nullptr};
+    LzPartRec* d_precs = nullptr;
+    LzPersistState* d_pst = nullptr;
+    long long* d_ptiming = nullptr;
+    std::vector<int32_t> h_rp;  // host copy of row_ptr (row partition)
 
     // reductions / selection
     double* d_partials = nullptr;
@@ -217,7 +226,8 @@ void free_all(macb_ctx* c) {
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
-                     c->d_sel_state, c->d_blockcnt, c->d_flush};
+                     c->d_sel_state, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs,
+                     c->d_pst, c->d_ptiming};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
@@ -316,6 +326,71 @@ void launch_lanczos_step(macb_ctx* c) {
     CK(cudaGetLastError());
 }
 
+template <int W>
+void launch_persist_w(macb_ctx* c, LzPersistArgs& a) {
+    void* params[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
+}
+
+// One cooperative launch = `nphases` fused Lanczos phases (kernels.cuh, k_lanczos_persist).
+void launch_persist(macb_ctx* c, int nphases) {
+    LzPersistArgs a;
+    a.n = c->n;
+    a.ld = c->ld;
+    a.nphases = nphases;
+    a.ncta = c->p_ncta;
+    a.rp = c->d_rp;
+    a.col = c->d_col;
+    a.val = c->d_val;
+    a.row_start = c->d_row_start;
+    a.sect[0] = c->d_sect[0];
+    a.sect[1] = c->d_sect[1];
+    a.basis = c->d_basis;
+    a.alpha = c->d_alpha;
+    a.beta = c->d_beta;
+    a.recs = c->d_precs;
+    a.st = c->d_pst;
+    a.timing = c->d_ptiming;
+    DISPATCH_W(c->W, launch_persist_w<WW>(c, a));
+    c->c_launches += 1;
+    c->c_spmv += nphases;
+    c->c_steps += nphases;
+}
+
+void setup_persist(macb_ctx* c) {
+    // CTAs: one per SM at most (cooperative launch => all co-resident); small graphs use fewer so that the
+    // grid barrier stays cheap.
+    int64_t want = ((int64_t)c->n * c->W + kPBlock - 1) / kPBlock;
+    c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
+    // contiguous row ranges balanced by the number of 4W-slot passes a row needs plus its length
+    const int n = c->n, W = c->W;
+    std::vector<int64_t> cost((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        int64_t len = c->h_rp[i + 1] - c->h_rp[i];
+        int64_t passes = std::max<int64_t>(1, (len + 4 * W - 1) / (4 * W));
+        cost[i + 1] = cost[i] + passes * 4 * W + len;
+    }
+    std::vector<int> rs((size_t)c->p_ncta + 1, n);
+    rs[0] = 0;
+    int row = 0;
+    for (int b = 1; b < c->p_ncta; ++b) {
+        const int64_t target = cost[n] * b / c->p_ncta;
+        while (row < n && cost[row] < target) ++row;
+        rs[b] = row;
+    }
+    c->d_row_start = dalloc<int>(c->p_ncta + 1);
+    CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d_sect[0] = dalloc<double>((size_t)c->n * 4);
+    c->d_sect[1] = dalloc<double>((size_t)c->n * 4);
+    c->d_precs = dalloc<LzPartRec>((size_t)c->p_ncta * 2);
+    c->d_pst = dalloc<LzPersistState>(1);
+    CK(cudaMemsetAsync(c->d_pst, 0, sizeof(LzPersistState), c->stream));
+#ifdef MACB_PTIMING
+    c->d_ptiming = dalloc<long long>((size_t)64 * c->p_ncta * 4);
+#endif
+}
+
 void ensure_basis(macb_ctx* c, int max_steps) {
     if (c->d_basis) return;
     double gb = 8.0;
@@ -333,6 +408,10 @@ void ensure_basis(macb_ctx* c, int max_steps) {
     c->d_coef = dalloc<double>(cap + 1);
     CK(cudaMallocHost(&c->h_alpha, sizeof(double) * (cap + 1)));
     CK(cudaMallocHost(&c->h_beta, sizeof(double) * (cap + 2)));
+    if (c->persist) {
+        setup_persist(c);
+        return;
+    }
     // capture kGraphSteps Lanczos steps (2 kernels each) into one graph
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -407,13 +486,20 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     for (int restart = 0; restart < 64; ++restart) {
         // ---- (re)start
         const double* src = use_warm ? c->d_v : c->d_x0;
-        CK(cudaMemcpyAsync(c->d_basis, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-        k_set_lanczos_start<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_beta, c->d_usum, use_warm ? 1.0 : c->x0_norm);
+        if (c->persist) {
+            k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs,
+                                                                         2 * c->p_ncta);
+        } else {
+            CK(cudaMemcpyAsync(c->d_basis, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+            k_set_lanczos_start<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_beta, c->d_usum, use_warm ? 1.0 : c->x0_norm);
+            c->h_beta[0] = use_warm ? 1.0 : c->x0_norm;
+        }
+        CK(cudaGetLastError());
         c->c_launches++;
-        c->h_beta[0] = use_warm ? 1.0 : c->x0_norm;
-        int k_done = 0;
+        int k_done = 0;      // size of the usable tridiagonal T_k (needs beta[0..k])
+        int phases = 0;      // persistent engine: phases run (phase j yields alpha[j], beta[j]) => k_done = phases - 1
         double theta_prev = std::numeric_limits<double>::infinity();
-// at most n - 1 steps per cycle: the Krylov space on 1-perp is exhausted by then, and a cycle
+        // at most n - 1 steps per cycle: the Krylov space on 1-perp is exhausted by then, and a cycle
         // that long without convergence is restarted from its Ritz vector below.
         const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
         bool invariant = false;
@@ -425,11 +511,21 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
                 batch = std::min(16 * kGraphSteps, ((k_done / 4) / kGraphSteps) * kGraphSteps);
             batch = std::min(batch, k_limit - k_done);
             if (batch > 0) {
-                run_lanczos_steps(c, batch);
-                CK(cudaMemcpyAsync(c->h_alpha + k_done, c->d_alpha + k_done, sizeof(double) * batch, cudaMemcpyDeviceToHost,
-                                   c->stream));
-                CK(cudaMemcpyAsync(c->h_beta + k_done + 1, c->d_beta + k_done + 1, sizeof(double) * batch,
-                                   cudaMemcpyDeviceToHost, c->stream));
+                if (c->persist) {
+                    const int run = batch + (phases == 0 ? 1 : 0);
+                    launch_persist(c, run);
+                    CK(cudaMemcpyAsync(c->h_alpha + phases, c->d_alpha + phases, sizeof(double) * run, cudaMemcpyDeviceToHost,
+                                       c->stream));
+                    CK(cudaMemcpyAsync(c->h_beta + phases, c->d_beta + phases, sizeof(double) * run, cudaMemcpyDeviceToHost,
+                                       c->stream));
+                    phases += run;
+                } else {
+                    run_lanczos_steps(c, batch);
+                    CK(cudaMemcpyAsync(c->h_alpha + k_done, c->d_alpha + k_done, sizeof(double) * batch, cudaMemcpyDeviceToHost,
+                                       c->stream));
+                    CK(cudaMemcpyAsync(c->h_beta + k_done + 1, c->d_beta + k_done + 1, sizeof(double) * batch,
+                                       cudaMemcpyDeviceToHost, c->stream));
+                }
                 CK(cudaStreamSynchronize(c->stream));
                 k_done += batch;
                 total_steps += batch;
@@ -612,6 +708,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         build_pattern(n, nf, fi, fj, m, ci, cj, rp, col, eid);
         c->nnz = (int64_t)col.size();
         c->W = pick_width((double)c->nnz / std::max(1, n));
+        c->h_rp = rp;
+        if (const char* env = getenv("MACB_LANCZOS")) c->persist = (std::string(env) != "graph");
 
         c->d_rp = dalloc<int>(n + 1);
         c->d_col = dalloc<int>(c->nnz);
@@ -945,6 +1043,17 @@ int macb_iter_ms(macb_handle h, double* ms, int cap, int* count) {
         for (int i = 0; i < std::min(cap, nrec); ++i) ms[i] = h->iter_ms[i];
     return MACB_OK;
 }
+
+#ifdef MACB_PTIMING
+extern "C" int macb_debug_ptiming(macb_handle h, long long* out /*[64][ncta][4]*/, int* ncta) {
+    return guarded(h, [&]() {
+        if (ncta) *ncta = h->p_ncta;
+        if (out && h->d_ptiming)
+            CK(cudaMemcpy(out, h->d_ptiming, sizeof(long long) * 64 * h->p_ncta * 4, cudaMemcpyDeviceToHost));
+        return (int)MACB_OK;
+    });
+}
+#endif
 
 int macb_device_sync(macb_handle h) {
     return guarded(h, [&]() {

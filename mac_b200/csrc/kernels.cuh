@@ -295,6 +295,264 @@ __global__ void __launch_bounds__(kBlock) k_lanczos_b(int n, int ld, double* __r
     }
 }
 
+// ---- K3 (persistent form): the whole Lanczos batch in ONE cooperative kernel -----------------------
+// State per node i is one 32-byte sector  S_i = (z_i, u_i, u'_i, diag_i)  with
+//     z = L u (un-normalised),  u = current Lanczos vector u_j,  u' = u_{j-1}.
+// The next vector is never materialised on its own: every consumer evaluates
+//     u_{j+1}[c] = k1 z_c + k2 u_c + k3 u'_c + k4,
+//     k1 = 1/beta_j, k2 = -alpha_j/beta_j, k3 = -beta_j/beta_{j-1}, k4 = -(mean of the rest)
+// from the gathered sector.  A gather of one double costs a 32-byte sector anyway, so packing the three
+// operands of the recurrence into that sector makes the fused form free in L2 traffic, and one Lanczos
+// step becomes ONE pass (gather + row sums) and ONE grid barrier (alpha_j, beta_j, sums).
+// Phase j computes u_j, z_j = L u_j and the partial sums  p1 = u.z, p2 = sum z, p3 = u.u, p4 = sum u;
+// after the barrier every CTA reduces the partials in the same fixed order, so all CTAs hold bitwise
+// identical alpha_j = p1/p3, beta_j = sqrt(p3).
+struct LzPersistState {
+    int phase;        // phases completed so far (= number of alpha/beta entries valid)
+    int cur;          // which sector buffer holds the input of the next phase
+    double k1, k2, k3, k4;
+    double beta_prev; // beta_{j-1} and sum(u_{j-1}) of the last completed phase j
+    double usum_prev;
+    unsigned int bar; // monotone barrier ticket counter
+    unsigned int pad;
+};
+
+// One record per CTA and phase parity: the CTA's four partial sums plus a tag (= phase + 1) published with
+// release semantics.  Polling every CTA's tag IS the grid barrier, and the data needed after the barrier
+// arrives with it -- one L2 round trip instead of fence + atomic + poll + a separate reduction pass.
+struct __align__(64) LzPartRec {
+    double p[4];
+    unsigned long long tag;
+    unsigned long long pad[3];
+};
+
+struct LzPersistArgs {
+    int n, ld, nphases, ncta;
+    const int* rp;
+    const int* col;
+    const double* val;
+    const int* row_start;   // [ncta + 1] contiguous row range per CTA, balanced by non-zeros
+    double* sect[2];        // two sector buffers, 4 doubles per node
+    double* basis;          // basis[j * ld + i] = u_j[i]
+    double* alpha;
+    double* beta;
+    LzPartRec* recs;        // [2][ncta]
+    LzPersistState* st;
+    long long* timing;      // debug (MACB_PTIMING builds): [phase][cta][4] clock64 stamps
+};
+
+__device__ __forceinline__ void ld_sector(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st_sector(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int ncta) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int old = atomicAdd(bar, 1u);
+        unsigned int target = (old / ncta + 1u) * ncta;
+        unsigned int cur;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while ((int)(cur - target) < 0);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Predicated sector gather: lanes whose slot is past the row end, or whose edge weight is exactly zero
+// (a candidate outside the current support -- most of the union pattern early in Frank-Wolfe), issue no
+// memory request at all.
+__device__ __forceinline__ void ld_sector_if(const double* p, bool pred, double& a, double& b, double& c) {
+    double d;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t"
+        "mov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+        "mov.f64 %2, 0d0000000000000000;\n\tmov.f64 %3, 0d0000000000000000;\n\t"
+        "@q ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+        : "l"(p), "r"((int)pred));
+}
+
+constexpr int kPBlock = 1024;
+constexpr int kPWarps = kPBlock / 32;
+
+template <int W>
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a) {
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double tot[4];
+    constexpr int rpw = 32 / W;                    // rows per warp per pass
+    const int lane = threadIdx.x & (W - 1);
+    const int sub = (threadIdx.x & 31) / W;
+    const int warp = threadIdx.x >> 5;
+    const int r0 = a.row_start[blockIdx.x], r1 = a.row_start[blockIdx.x + 1];
+    const int* __restrict__ col = a.col;
+    const double* __restrict__ val = a.val;
+    const int* __restrict__ rp = a.rp;
+
+    int phase = a.st->phase;
+    int cur = a.st->cur;
+    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;
+
+    for (int it = 0; it < a.nphases; ++it, ++phase) {
+        const double* __restrict__ S = a.sect[cur];
+        double* __restrict__ D = a.sect[cur ^ 1];
+        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+#ifdef MACB_PTIMING
+        long long t_start = clock64();
+#endif
+        for (int base = r0 + warp * rpw; base < r1; base += kPWarps * rpw) {
+            const int row = base + sub;
+            const bool valid = row < r1;
+            double acc0 = 0.0, acc1 = 0.0;
+            double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;   // the row's own sector, requested before the gathers
+            if (valid && lane == 0) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
+            if (valid) {
+                const int s1 = rp[row + 1];
+                for (int s = rp[row] + lane; s < s1; s += 4 * W) {
+                    // four slots per lane in flight; out-of-row slots re-read slot s (same line) with weight 0
+                    const bool v1 = s + W < s1, v2 = s + 2 * W < s1, v3 = s + 3 * W < s1;
+                    const int i1 = v1 ? s + W : s, i2 = v2 ? s + 2 * W : s, i3 = v3 ? s + 3 * W : s;
+                    const int c0 = ld_nc(col + s), c1 = ld_nc(col + i1), c2 = ld_nc(col + i2), c3 = ld_nc(col + i3);
+                    const double w0 = ld_nc(val + s);
+                    const double w1 = v1 ? ld_nc(val + i1) : 0.0, w2 = v2 ? ld_nc(val + i2) : 0.0,
+                                 w3 = v3 ? ld_nc(val + i3) : 0.0;
+                    double z0, u0, q0, z1, u1, q1, z2, u2, q2, z3, u3, q3;
+                    ld_sector_if(S + 4 * (size_t)c0, w0 != 0.0, z0, u0, q0);
+                    ld_sector_if(S + 4 * (size_t)c1, w1 != 0.0, z1, u1, q1);
+                    ld_sector_if(S + 4 * (size_t)c2, w2 != 0.0, z2, u2, q2);
+                    ld_sector_if(S + 4 * (size_t)c3, w3 != 0.0, z3, u3, q3);
+                    // sum_s w_s (u_next[c_s] - k4) ; the constant k4 is folded back through diag below
+                    acc0 = fma(w0, fma(k1, z0, fma(k2, u0, k3 * q0)), acc0);
+                    acc1 = fma(w1, fma(k1, z1, fma(k2, u1, k3 * q1)), acc1);
+                    acc0 = fma(w2, fma(k1, z2, fma(k2, u2, k3 * q2)), acc0);
+                    acc1 = fma(w3, fma(k1, z3, fma(k2, u3, k3 * q3)), acc1);
+                }
+            }
+            acc0 += acc1;
+#pragma unroll
+            for (int o = W / 2; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            if (valid && lane == 0) {
+                const double z = oz, u = ou, q = oq, d = od;
+                const double t = fma(k1, z, fma(k2, u, k3 * q));
+                const double un = t + k4;                                    // u_phase[row]
+                const double zn = fma(d, t, -acc0);                         // (L u_phase)[row]; L 1 = 0 cancels k4
+                st_sector(D + 4 * (size_t)row, zn, un, u, d);
+                bj[row] = un;
+                p1 = fma(un, zn, p1);
+                p2 += zn;
+                p3 = fma(un, un, p3);
+                p4 += un;
+            }
+        }
+        // ---- CTA partials -> tagged record; poll all records (= grid barrier); same fixed-order sum everywhere
+        double v[4] = {p1, p2, p3, p4};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sm[i * kPWarps + warp] = v[i];
+        __syncthreads();   // all row results of this CTA are written (sector buffer, basis) before the tag below
+#ifdef MACB_PTIMING
+        long long t_rows = clock64();
+#endif
+        LzPartRec* recs = a.recs + (size_t)(phase & 1) * a.ncta;
+        const unsigned long long want = (unsigned long long)phase + 1ull;
+        if (warp == 0) {
+            double x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] = sm[i * kPWarps + (threadIdx.x & 31)];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_xor_sync(0xffffffffu, x[i], o);
+            }
+            // arrive: publish the record, then one release-add on the shared counter; wait: poll that ONE counter
+            // (a per-CTA flag poll would put ncta^2 readers on the L2), then fetch all records in one round trip.
+            if (threadIdx.x == 0) {
+                st_sector(recs[blockIdx.x].p, x[0], x[1], x[2], x[3]);
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.st->bar) : "memory");
+                const unsigned int target = (unsigned int)want * (unsigned int)a.ncta;
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&a.st->bar) : "memory");
+                } while ((int)(seen - target) < 0);
+            }
+            __syncwarp();
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            for (int b = (threadIdx.x & 31); b < a.ncta; b += 32) {
+                double q0, q1, q2, q3;
+                ld_sector(recs[b].p, q0, q1, q2, q3);
+                y0 += q0; y1 += q1; y2 += q2; y3 += q3;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, o);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, o);
+                y2 += __shfl_xor_sync(0xffffffffu, y2, o);
+                y3 += __shfl_xor_sync(0xffffffffu, y3, o);
+            }
+            if (threadIdx.x == 0) {
+                tot[0] = y0; tot[1] = y1; tot[2] = y2; tot[3] = y3;
+            }
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        long long t_bar = clock64();
+#endif
+        const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
+        const double beta = sqrt(P3);
+        const double binv = safe_inv(beta);
+        const double alpha = P1 * binv * binv;
+        const double nk1 = binv, nk2 = -alpha * binv, nk3 = (phase > 0) ? -beta * safe_inv(beta_prev) : 0.0;
+        const double nk4 = -(nk1 * P2 + nk2 * P4 + nk3 * usum_prev) / (double)a.n;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.alpha[phase] = alpha;
+            a.beta[phase] = beta;
+        }
+#ifdef MACB_PTIMING
+        if (threadIdx.x == 0 && a.timing && it < 64) {
+            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            t[0] = t_start; t[1] = t_rows; t[2] = t_bar; t[3] = clock64();
+        }
+#endif
+        k1 = nk1; k2 = nk2; k3 = nk3; k4 = nk4;
+        beta_prev = beta;
+        usum_prev = P4;
+        cur ^= 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.st->phase = phase;
+        a.st->cur = cur;
+        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
+        a.st->beta_prev = beta_prev;
+        a.st->usum_prev = usum_prev;
+    }
+}
+
+// sectors for phase 0: (0, src_i, 0, diag_i) with (k1,k2,k3,k4) = (0,1,0,0)  =>  u_0 = src
+__global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double* __restrict__ src,
+                                                            const double* __restrict__ diag, double* __restrict__ sect0,
+                                                            LzPersistState* st, LzPartRec* recs, int nrecs) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        st_sector(sect0 + 4 * (size_t)i, 0.0, src[i], 0.0, diag[i]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrecs; i += gridDim.x * blockDim.x) recs[i].tag = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->phase = 0;
+        st->cur = 0;
+        st->k1 = 0.0; st->k2 = 1.0; st->k3 = 0.0; st->k4 = 0.0;
+        st->beta_prev = 0.0;
+        st->usum_prev = 0.0;
+        st->bar = 0u;
+    }
+}
+
 // ---- finalisation: Ritz vector, normalisation, residual ------------------------------------------
 // y_raw = sum_t coef[t] basis[t]   (coef[t] = s_t / beta[t] folds the normalisation of u_t)
 __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const double* __restrict__ basis,

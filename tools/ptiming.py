@@ -1,0 +1,30 @@
+"""Per-phase timing breakdown of the persistent Lanczos kernel (needs `make timing`; run with
+MACB_LIB=mac_b200/libmacb200_timing.so).  Scratch tool."""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mac_b200 import synth, _lib
+from mac_b200.solvers import MAC
+which = sys.argv[1] if len(sys.argv) > 1 else "H"
+if which == "H":
+    fixed, cand, n, k, x0 = synth.headline()
+elif which == "dense":
+    fixed, cand, n, k, x0 = synth.headline(); x0 = np.full(len(x0), 0.2)
+else:
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", f"g2o_{which}.npz"))
+    from mac_b200.g2o import split_edges
+    fixed, cand = split_edges(z["i"], z["j"], z["kappa"]); n = int(z["n"]); x0 = np.ones(len(cand[0])) * 0.3
+mac = MAC(fixed, cand, n)
+lam, v = mac.fiedler_pair(x0)
+print(which, "lambda2", lam, mac.last_info, mac._h.sizes())
+L = _lib.lib()
+ncta = C.c_int()
+L.macb_debug_ptiming(mac._h._h, None, C.byref(ncta))
+buf = np.zeros((64, ncta.value, 4), dtype=np.int64)
+L.macb_debug_ptiming(mac._h._h, buf.ctypes.data_as(C.c_void_p), C.byref(ncta))
+t = buf[2:33].astype(np.float64)   # phases of the last launch (skip first two)
+rows = t[:, :, 1] - t[:, :, 0]; bar = t[:, :, 2] - t[:, :, 1]; red = t[:, :, 3] - t[:, :, 2]
+print("ncta", ncta.value)
+print("cycles per phase (mean over phases): rows mean %.0f max %.0f min %.0f | barrier wait mean %.0f min %.0f | reduce mean %.0f" % (
+    rows.mean(), rows.max(axis=1).mean(), rows.min(axis=1).mean(), bar.mean(), bar.min(axis=1).mean(), red.mean()))
+print("total per phase (cta 0):", np.diff(t[:, 0, 0]).mean())
