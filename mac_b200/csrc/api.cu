@@ -497,6 +497,9 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         CK(cudaGetLastError());
         c->c_launches++;
         int k_done = 0;      // size of the usable tridiagonal T_k (needs beta[0..k])
+        int k_a = 0, k_b = 0;            // last two convergence checks: (k, residual estimate)
+        double est_a = 0.0, est_b = 0.0, theta_delta = -1.0;
+        bool resid_miss = false;
         int phases = 0;      // persistent engine: phases run (phase j yields alpha[j], beta[j]) => k_done = phases - 1
         double theta_prev = std::numeric_limits<double>::infinity();
         // at most n - 1 steps per cycle: the Krylov space on 1-perp is exhausted by then, and a cycle
@@ -504,11 +507,27 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
         bool invariant = false;
         while (true) {
+            // Batch size: the residual estimate of the smallest Ritz pair decays geometrically once the pair is
+            // resolved, so two checks predict where it will cross the tolerance.  Every check costs a host round
+            // trip plus a tridiagonal eigen-solve, so fewer is better.  The schedule depends only on this solve's
+            // own data (no cross-solve history), which keeps a solve a pure function of (L(x), start vector).
             int batch;
-            if (k_done < 4 * kGraphSteps)
+            if (k_done == 0) {
                 batch = kGraphSteps;
-            else
-                batch = std::min(16 * kGraphSteps, ((k_done / 4) / kGraphSteps) * kGraphSteps);
+            } else {
+                batch = (k_done < 4 * kGraphSteps) ? kGraphSteps
+                                                   : std::min(16 * kGraphSteps, ((k_done / 4) / kGraphSteps) * kGraphSteps);
+                if (resid_miss) {
+                    batch = std::max(8, k_done / 16);
+                } else if (k_b > k_a && est_a > 0.0 && est_b > 0.0) {
+                    const double slope = (std::log(est_b) - std::log(est_a)) / (double)(k_b - k_a);
+                    const double target = 0.5 * tol * lnorm / sqrtn;
+                    if (slope < -1e-4 && est_b > target) {
+                        const double pred = (std::log(target) - std::log(est_b)) / slope;
+                        batch = (int)std::min<double>(std::max(8.0, std::ceil(1.05 * pred) + 2.0), (double)std::max(kGraphSteps, k_done));
+                    }
+                }
+            }
             batch = std::min(batch, k_limit - k_done);
             if (batch > 0) {
                 if (c->persist) {
@@ -539,11 +558,19 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
                     break;
                 }
             if (k == 0) throw ArgFail{"macb_fiedler: Lanczos made no progress", MACB_ERR_STATE};
-            const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k, invariant ? std::numeric_limits<double>::infinity() : theta_prev);
+            const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k,
+                                                        invariant ? std::numeric_limits<double>::infinity() : theta_prev,
+                                                        theta_delta);
             s.resize(k);
             tridiag_vector(c->h_alpha, c->h_beta, k, theta, s.data());
+            if (std::isfinite(theta_prev)) theta_delta = 2.0 * std::fabs(theta_prev - theta);
             theta_prev = theta;
             const double est = std::fabs(c->h_beta[k]) * std::fabs(s[k - 1]);
+            k_a = k_b;
+            est_a = est_b;
+            k_b = k;
+            est_b = est;
+            resid_miss = false;
             const bool exhausted = invariant || k_done >= k_limit;
             if (est * sqrtn < tol * lnorm || exhausted) {
                 finalize_ritz(c, k, s, out);
@@ -553,6 +580,7 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
                     c->have_v = true;
                     return MACB_OK;
                 }
+                resid_miss = true;
                 if (exhausted) break;  // restart from the best Ritz vector (now in d_v)
             }
         }

@@ -31,7 +31,7 @@ inline bool has_eig_below(const double* a, const double* b2, int k, double x, do
 
 }  // namespace
 
-double tridiag_smallest_value(const double* a, const double* b, int k, double hint_hi) {
+double tridiag_smallest_value(const double* a, const double* b, int k, double hint_hi, double hint_delta) {
     if (k <= 0) return 0.0;
     if (k == 1) return a[0];
     std::vector<double> b2(k);
@@ -52,14 +52,34 @@ double tridiag_smallest_value(const double* a, const double* b, int k, double hi
     const double tnorm = std::max(std::fabs(gl), std::fabs(gu));
     double lo = gl - 2.0 * DBL_EPSILON * tnorm * k - 2.0 * pivmin;
     double hi = gu + 2.0 * DBL_EPSILON * tnorm * k + 2.0 * pivmin;
-    if (std::isfinite(hint_hi)) {
-        double h = hint_hi + 8.0 * DBL_EPSILON * tnorm;
-        if (h < hi && has_eig_below(a, b2.data(), k, h, pivmin)) hi = h;
-    }
     // smallest diagonal entry is an upper bound on the smallest eigenvalue
     double amin = a[0];
     for (int i = 1; i < k; ++i) amin = std::min(amin, a[i]);
-    if (amin + 4.0 * DBL_EPSILON * tnorm < hi) hi = amin + 4.0 * DBL_EPSILON * tnorm;
+    hi = std::min(hi, amin + 4.0 * DBL_EPSILON * tnorm);
+    bool warm = false;
+    if (std::isfinite(hint_hi)) {
+        double h = hint_hi + 8.0 * DBL_EPSILON * tnorm;
+        if (h < hi && has_eig_below(a, b2.data(), k, h, pivmin)) {
+            hi = h;
+            warm = true;
+        }
+    }
+    if (warm) {
+        // walk down from hi in growing strides until the interval below holds no eigenvalue
+        double delta = (hint_delta > 0.0) ? hint_delta : 1e-6 * std::max(std::fabs(hi), 1e-300);
+        delta = std::max(delta, 16.0 * DBL_EPSILON * tnorm);
+        for (int it = 0; it < 64; ++it) {
+            double x = hi - delta;
+            if (x <= lo) break;
+            if (has_eig_below(a, b2.data(), k, x, pivmin)) {
+                hi = x;
+                delta *= 8.0;
+            } else {
+                lo = x;
+                break;
+            }
+        }
+    }
     for (int it = 0; it < 200; ++it) {
         double mid = 0.5 * (lo + hi);
         if (!(hi - lo > 2.0 * DBL_EPSILON * std::max(std::fabs(lo), std::fabs(hi)) + 2.0 * pivmin)) break;
