@@ -83,6 +83,11 @@ struct macb_ctx {
     cudaGraphExec_t lz_graph = nullptr;
     // persistent engine
     bool persist = true;
+    bool persist_stream = false;
+    bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
+    double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
+    int* h_stop = nullptr;         // host-mapped
+    int ab_dirty = 0;              // h_ab entries [0, ab_dirty) may hold values of an earlier launch
     int p_ncta = 1;
     int* d_row_start = nullptr;
     double* d_sect[2] = {nullptr, nullptr};
@@ -234,6 +239,8 @@ void free_all(macb_ctx* c) {
     if (c->h_beta) cudaFreeHost(c->h_beta);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
+    if (c->h_ab) cudaFreeHost(c->h_ab);
+    if (c->h_stop) cudaFreeHost(c->h_stop);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->it0) cudaEventDestroy(c->it0);
@@ -329,11 +336,14 @@ void launch_lanczos_step(macb_ctx* c) {
 template <int W>
 void launch_persist_w(macb_ctx* c, LzPersistArgs& a) {
     void* params[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
+    if (c->persist_stream)
+        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W, true>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
+    else
+        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W, false>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
 }
 
 // One cooperative launch = `nphases` fused Lanczos phases (kernels.cuh, k_lanczos_persist).
-void launch_persist(macb_ctx* c, int nphases) {
+void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     LzPersistArgs a;
     a.n = c->n;
     a.ld = c->ld;
@@ -351,10 +361,14 @@ void launch_persist(macb_ctx* c, int nphases) {
     a.recs = c->d_precs;
     a.st = c->d_pst;
     a.timing = c->d_ptiming;
+    a.ab_host = async ? c->h_ab : nullptr;
+    a.stop = async ? c->h_stop : nullptr;
     DISPATCH_W(c->W, launch_persist_w<WW>(c, a));
     c->c_launches += 1;
-    c->c_spmv += nphases;
-    c->c_steps += nphases;
+    if (!async) {
+        c->c_spmv += nphases;
+        c->c_steps += nphases;
+    }
 }
 
 void setup_persist(macb_ctx* c) {
@@ -386,6 +400,10 @@ void setup_persist(macb_ctx* c) {
     c->d_precs = dalloc<LzPartRec>((size_t)c->p_ncta * 2);
     c->d_pst = dalloc<LzPersistState>(1);
     CK(cudaMemsetAsync(c->d_pst, 0, sizeof(LzPersistState), c->stream));
+    CK(cudaHostAlloc(&c->h_ab, sizeof(double) * 2 * (c->basis_cap + 2), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&c->h_stop, sizeof(int) * 16, cudaHostAllocMapped));
+    *c->h_stop = 0;
+    for (int64_t j = 0; j < 2 * (c->basis_cap + 2); ++j) c->h_ab[j] = std::numeric_limits<double>::quiet_NaN();
 #ifdef MACB_PTIMING
     c->d_ptiming = dalloc<long long>((size_t)64 * c->p_ncta * 4);
 #endif
@@ -457,6 +475,106 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
     out.resid = c->h_sc->res1 / (std::sqrt(c->h_sc->vv) * c->lnorm);
 }
 
+
+// Check points of the asynchronous Rayleigh-Ritz: a function of k alone, so that the step count at which a solve
+// stops -- and with it the result, to the last bit -- does not depend on host/device timing.
+inline int next_check(int k) { return k + std::max(16, 16 * (k / 256)); }
+
+// One Lanczos cycle on the persistent engine with the host Rayleigh-Ritz running concurrently with the kernel.
+// Returns: 1 converged (result in `out`, vector in d_v), 0 cycle exhausted without convergence (best Ritz vector
+// in d_v), and updates total_steps.
+int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& total_steps, std::vector<double>& s,
+                        FiedlerResult& out) {
+    const int n = c->n;
+    const double sqrtn = std::sqrt((double)n), lnorm = c->lnorm;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    volatile double* ab = c->h_ab;
+    int phases_done = 0;   // phases the device has completed in earlier launches of this cycle
+    int k_next = std::min(16, k_limit);
+    int k_seen = 0;        // alpha/beta copied into h_alpha/h_beta for indices < k_seen
+    double theta_prev = std::numeric_limits<double>::infinity(), theta_delta = -1.0;
+    bool invariant = false;
+    while (true) {
+        // ---- launch (or resume) the kernel for everything that is left of this cycle
+        const int nph = (k_limit + 1) - phases_done;
+        if (nph > 0) {
+            // entries at and beyond the resume point that an earlier solve / launch may have written
+            for (int j = phases_done; j < std::min(c->ab_dirty, k_limit + 1); ++j) {
+                ab[2 * j] = nan;
+                ab[2 * j + 1] = nan;
+            }
+            c->ab_dirty = phases_done;
+            *(volatile int*)c->h_stop = 0;
+            launch_persist(c, nph, true);
+        }
+        bool stopped = false;
+        int k_conv = -1;
+        while (!stopped) {
+            // wait for beta[k_next] (phase k_next) or for the kernel to end
+            const int need = std::min(k_next, k_limit);
+            bool kernel_done = false;
+            while (std::isnan(ab[2 * need + 1])) {
+                if (cudaStreamQuery(c->stream) != cudaErrorNotReady) {
+                    kernel_done = true;
+                    break;
+                }
+            }
+            if (kernel_done && std::isnan(ab[2 * need + 1])) {
+                CK(cudaStreamSynchronize(c->stream));  // surfaces launch/runtime errors
+                if (std::isnan(ab[2 * need + 1])) throw ArgFail{"macb_fiedler: Lanczos kernel ended early", MACB_ERR_STATE};
+            }
+            for (int j = k_seen; j <= need; ++j) {
+                c->h_alpha[j] = ab[2 * j];
+                c->h_beta[j] = ab[2 * j + 1];
+            }
+            k_seen = std::max(k_seen, need + 1);
+            int k = need;
+            for (int j = 1; j <= need; ++j)
+                if (!(c->h_beta[j] > brk)) {
+                    k = j;
+                    invariant = true;
+                    break;
+                }
+            if (k == 0) throw ArgFail{"macb_fiedler: Lanczos made no progress", MACB_ERR_STATE};
+            const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k,
+                                                        invariant ? std::numeric_limits<double>::infinity() : theta_prev, theta_delta);
+            s.resize(k);
+            tridiag_vector(c->h_alpha, c->h_beta, k, theta, s.data());
+            if (std::isfinite(theta_prev)) theta_delta = 2.0 * std::fabs(theta_prev - theta);
+            theta_prev = theta;
+            const double est = std::fabs(c->h_beta[k]) * std::fabs(s[k - 1]);
+            const bool exhausted = invariant || need >= k_limit;
+            if (est * sqrtn < tol * lnorm || exhausted) {
+                *(volatile int*)c->h_stop = 1;
+                CK(cudaStreamSynchronize(c->stream));
+                CK(cudaMemcpy(&phases_done, &c->d_pst->phase, sizeof(int), cudaMemcpyDeviceToHost));
+                c->ab_dirty = std::max(c->ab_dirty, phases_done);
+                stopped = true;
+                k_conv = k;
+                finalize_ritz(c, k, s, out);
+                if (out.resid < tol) {
+                    total_steps += phases_done;
+                    c->c_steps += phases_done;
+                    c->c_spmv += phases_done;
+                    out.converged = true;
+                    return 1;
+                }
+                if (exhausted || phases_done >= k_limit + 1) {
+                    total_steps += phases_done;
+                    c->c_steps += phases_done;
+                    c->c_spmv += phases_done;
+                    return invariant ? -1 : 0;
+                }
+                // estimate passed but the true residual did not: resume the kernel and look again a little later
+                k_next = next_check(need);
+            } else {
+                k_next = next_check(need);
+            }
+        }
+        (void)k_conv;
+    }
+}
+
 // Deflated Lanczos on P L(x) P.  Replaces nx:149-253 (see macb200.h).
 int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult& out) {
     if (!c->have_x) throw ArgFail{"macb_fiedler: call macb_set_x first", MACB_ERR_STATE};
@@ -496,6 +614,16 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         }
         CK(cudaGetLastError());
         c->c_launches++;
+        if (c->persist && c->async_rr) {
+            const int k_lim = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
+            const int rc = lanczos_cycle_async(c, tol, k_lim, brk, total_steps, s, out);
+            out.steps = total_steps;
+            c->have_v = true;
+            if (rc == 1) return MACB_OK;
+            use_warm = true;
+            if (rc < 0 || total_steps >= max_steps) break;
+            continue;
+        }
         int k_done = 0;      // size of the usable tridiagonal T_k (needs beta[0..k])
         int k_a = 0, k_b = 0;            // last two convergence checks: (k, residual estimate)
         double est_a = 0.0, est_b = 0.0, theta_delta = -1.0;
@@ -738,6 +866,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         c->W = pick_width((double)c->nnz / std::max(1, n));
         c->h_rp = rp;
         if (const char* env = getenv("MACB_LANCZOS")) c->persist = (std::string(env) != "graph");
+        if (const char* env = getenv("MACB_PERSIST_STREAM")) c->persist_stream = atoi(env) != 0;
+        if (const char* env = getenv("MACB_ASYNC")) c->async_rr = atoi(env) != 0;
 
         c->d_rp = dalloc<int>(n + 1);
         c->d_col = dalloc<int>(c->nnz);

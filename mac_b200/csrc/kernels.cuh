@@ -339,6 +339,11 @@ struct LzPersistArgs {
     LzPartRec* recs;        // [2][ncta]
     LzPersistState* st;
     long long* timing;      // debug (MACB_PTIMING builds): [phase][cta][4] clock64 stamps
+    // Asynchronous Rayleigh-Ritz: (alpha_j, beta_j) are streamed into host-mapped memory as they are produced and
+    // the host raises *stop (host-mapped) once the Ritz pair has converged; CTA 0 samples it once per phase and
+    // publishes its decision with its partial-sum record, so all CTAs leave after the same phase.
+    double* ab_host;        // [2 * phase] = alpha, [2 * phase + 1] = beta   (may be nullptr)
+    const int* stop;        // (may be nullptr)
 };
 
 __device__ __forceinline__ void ld_sector(const double* p, double& a, double& b, double& c, double& d) {
@@ -380,10 +385,17 @@ __device__ __forceinline__ void ld_sector_if(const double* p, bool pred, double&
 constexpr int kPBlock = 1024;
 constexpr int kPWarps = kPBlock / 32;
 
-template <int W>
+// STREAM = false: each sub-warp of W lanes walks its own row (W-strided segments of col/val).
+// STREAM = true : the warp reads the contiguous slot range of its rpw rows in fully coalesced 32-slot chunks
+//                 (4 chunks in flight), stages the products w_s * u_next[c_s] in shared memory, and the sub-warps
+//                 then sum their rows' segments from there ("CSR-stream" at warp granularity).  Same arithmetic,
+//                 ~3x fewer L1TEX wavefronts for the streamed (col, val) data.
+template <int W, bool STREAM>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a) {
     __shared__ double sm[4 * kPWarps];
     __shared__ double tot[4];
+    __shared__ int stop_sm;
+    __shared__ double stage[STREAM ? kPWarps * 128 : 1];
     constexpr int rpw = 32 / W;                    // rows per warp per pass
     const int lane = threadIdx.x & (W - 1);
     const int sub = (threadIdx.x & 31) / W;
@@ -403,6 +415,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
         double* __restrict__ D = a.sect[cur ^ 1];
         double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
         double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+        int stop_now = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.stop)
+            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_now) : "l"(a.stop));
 #ifdef MACB_PTIMING
         long long t_start = clock64();
 #endif
@@ -412,7 +427,33 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
             double acc0 = 0.0, acc1 = 0.0;
             double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;   // the row's own sector, requested before the gathers
             if (valid && lane == 0) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
-            if (valid) {
+            if (STREAM) {
+                double* __restrict__ st = stage + warp * 128;
+                const int wl = threadIdx.x & 31;
+                const int rs = valid ? rp[row] : 0, re = valid ? rp[row + 1] : 0;
+                const int sA = rp[base], sB = rp[min(base + rpw, r1)];
+                for (int t0 = sA; t0 < sB; t0 += 128) {
+                    const int i0 = t0 + wl, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+                    const bool v0 = i0 < sB, v1 = i1 < sB, v2 = i2 < sB, v3 = i3 < sB;
+                    const int c0 = v0 ? ld_nc(col + i0) : 0, c1 = v1 ? ld_nc(col + i1) : 0, c2 = v2 ? ld_nc(col + i2) : 0,
+                              c3 = v3 ? ld_nc(col + i3) : 0;
+                    const double w0 = v0 ? ld_nc(val + i0) : 0.0, w1 = v1 ? ld_nc(val + i1) : 0.0,
+                                 w2 = v2 ? ld_nc(val + i2) : 0.0, w3 = v3 ? ld_nc(val + i3) : 0.0;
+                    double z0, u0, q0, z1, u1, q1, z2, u2, q2, z3, u3, q3;
+                    ld_sector_if(S + 4 * (size_t)c0, w0 != 0.0, z0, u0, q0);
+                    ld_sector_if(S + 4 * (size_t)c1, w1 != 0.0, z1, u1, q1);
+                    ld_sector_if(S + 4 * (size_t)c2, w2 != 0.0, z2, u2, q2);
+                    ld_sector_if(S + 4 * (size_t)c3, w3 != 0.0, z3, u3, q3);
+                    st[wl] = w0 * fma(k1, z0, fma(k2, u0, k3 * q0));
+                    st[wl + 32] = w1 * fma(k1, z1, fma(k2, u1, k3 * q1));
+                    st[wl + 64] = w2 * fma(k1, z2, fma(k2, u2, k3 * q2));
+                    st[wl + 96] = w3 * fma(k1, z3, fma(k2, u3, k3 * q3));
+                    __syncwarp();
+                    const int lo = max(rs, t0) - t0, hi = min(re, t0 + 128) - t0;
+                    for (int i = lo + lane; i < hi; i += W) acc0 += st[i];
+                    __syncwarp();
+                }
+            } else if (valid) {
                 const int s1 = rp[row + 1];
                 for (int s = rp[row] + lane; s < s1; s += 4 * W) {
                     // four slots per lane in flight; out-of-row slots re-read slot s (same line) with weight 0
@@ -477,6 +518,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
             // (a per-CTA flag poll would put ncta^2 readers on the L2), then fetch all records in one round trip.
             if (threadIdx.x == 0) {
                 st_sector(recs[blockIdx.x].p, x[0], x[1], x[2], x[3]);
+                if (blockIdx.x == 0) __stcg(&recs[0].pad[0], (unsigned long long)stop_now);
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.st->bar) : "memory");
                 const unsigned int target = (unsigned int)want * (unsigned int)a.ncta;
                 unsigned int seen;
@@ -500,6 +542,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
             }
             if (threadIdx.x == 0) {
                 tot[0] = y0; tot[1] = y1; tot[2] = y2; tot[3] = y3;
+                stop_sm = (int)__ldcg(&recs[0].pad[0]);
             }
         }
         __syncthreads();
@@ -507,6 +550,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
         long long t_bar = clock64();
 #endif
         const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
+        const int stop_all = stop_sm;
         const double beta = sqrt(P3);
         const double binv = safe_inv(beta);
         const double alpha = P1 * binv * binv;
@@ -515,6 +559,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             a.alpha[phase] = alpha;
             a.beta[phase] = beta;
+            if (a.ab_host)   // one 16-byte posted write: the host sees alpha and beta together
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(alpha), "d"(beta) : "memory");
         }
 #ifdef MACB_PTIMING
         if (threadIdx.x == 0 && a.timing && it < 64) {
@@ -526,6 +572,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
         beta_prev = beta;
         usum_prev = P4;
         cur ^= 1;
+        if (stop_all) {
+            ++phase;
+            break;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.st->phase = phase;

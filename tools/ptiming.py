@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mac_b200 import synth, _lib
 from mac_b200.solvers import MAC
 which = sys.argv[1] if len(sys.argv) > 1 else "H"
+print("stream", os.environ.get("MACB_PERSIST_STREAM", "1"))
 if which == "H":
     fixed, cand, n, k, x0 = synth.headline()
 elif which == "dense":
