@@ -139,6 +139,11 @@ int macb_l2_flush(macb_handle h);
 int macb_set_bench(macb_handle h, int time_iters, int flush_l2_between_iters);
 int macb_iter_ms(macb_handle h, double* ms, int cap, int* count);
 
+/* Bench mode only (macb_set_bench time_iters != 0): cumulative CUDA-event time of the Lanczos kernel launches
+ * (events recorded on the handle's stream around each launch), the Lanczos steps they ran, and the algorithmic
+ * bytes of one step.  This is the dominant kernel of the path; bench.py derives its roofline line from it. */
+int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double* algo_bytes_per_phase);
+
 /* cudaDeviceSynchronize on the handle's device. */
 int macb_device_sync(macb_handle h);
 

@@ -84,6 +84,9 @@ struct macb_ctx {
     // persistent engine
     bool persist = true;
     bool persist_stream = false;
+    int persist_v = 3;             // 3: slot-parallel kernel (k_lanczos_slots); 1: row-parallel (k_lanczos_persist)
+    int *d_chunk_ptr = nullptr, *d_chunk_row = nullptr;
+    size_t slots_smem = 0;
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
     int* h_stop = nullptr;         // host-mapped
@@ -107,11 +110,15 @@ struct macb_ctx {
     void* d_flush = nullptr;
 
     bool have_x = false, have_v = false, have_g = false, have_sel = false;
+    bool have_prev_v = false;  // d_v holds a (possibly stale) Fiedler vector usable as a warm start
     double lnorm = 0.0;
     int64_t nnz_active = 0;
     double min_sel_tol = 1e-10;
 
     int64_t c_launches = 0, c_spmv = 0, c_steps = 0, c_solves = 0;
+    double lz_kernel_ms = 0.0;     // CUDA-event time of the Lanczos kernels (bench mode only)
+    int64_t lz_kernel_phases = 0;
+    cudaEvent_t lz0 = nullptr, lz1 = nullptr;
     double phase_ms[MACB_T_COUNT] = {0, 0, 0, 0, 0, 0};
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -231,7 +238,7 @@ void free_all(macb_ctx* c) {
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
-                     c->d_sel_state, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs,
+                     c->d_sel_state, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
                      c->d_pst, c->d_ptiming};
     for (void* p : dptrs)
         if (p) cudaFree(p);
@@ -245,6 +252,8 @@ void free_all(macb_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->it0) cudaEventDestroy(c->it0);
     if (c->it1) cudaEventDestroy(c->it1);
+    if (c->lz0) cudaEventDestroy(c->lz0);
+    if (c->lz1) cudaEventDestroy(c->lz1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -363,7 +372,15 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.timing = c->d_ptiming;
     a.ab_host = async ? c->h_ab : nullptr;
     a.stop = async ? c->h_stop : nullptr;
-    DISPATCH_W(c->W, launch_persist_w<WW>(c, a));
+    if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
+    if (c->persist_v == 3) {
+        LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row};
+        void* params[] = {&a, &ch};
+        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_slots, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
+    } else {
+        DISPATCH_W(c->W, launch_persist_w<WW>(c, a));
+    }
+    if (c->bench_time_iters) CK(cudaEventRecord(c->lz1, c->stream));
     c->c_launches += 1;
     if (!async) {
         c->c_spmv += nphases;
@@ -372,25 +389,73 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
 }
 
 void setup_persist(macb_ctx* c) {
-    // CTAs: one per SM at most (cooperative launch => all co-resident); small graphs use fewer so that the
-    // grid barrier stays cheap.
-    int64_t want = ((int64_t)c->n * c->W + kPBlock - 1) / kPBlock;
-    c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
-    // contiguous row ranges balanced by the number of 4W-slot passes a row needs plus its length
     const int n = c->n, W = c->W;
-    std::vector<int64_t> cost((size_t)n + 1, 0);
-    for (int i = 0; i < n; ++i) {
-        int64_t len = c->h_rp[i + 1] - c->h_rp[i];
-        int64_t passes = std::max<int64_t>(1, (len + 4 * W - 1) / (4 * W));
-        cost[i + 1] = cost[i] + passes * 4 * W + len;
+    std::vector<int> rs;
+    if (c->persist_v == 3) {
+        // slot-parallel kernel: CTAs sized by work (one slot = 1, one row = 4), chunks of <= kPBlock rows and
+        // <= cap slots so that a chunk's products fit in shared memory
+        const int64_t cap = (227 * 1024 - 4096) / 8;
+        int64_t maxrow = 0;
+        for (int i = 0; i < n; ++i) maxrow = std::max<int64_t>(maxrow, c->h_rp[i + 1] - c->h_rp[i]);
+        if (maxrow > cap) {
+            c->persist_v = 1;   // a single row does not fit the staging buffer: use the row-parallel kernel
+        } else {
+            const int64_t total = (int64_t)c->nnz + 4 * (int64_t)n;
+            c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>((total + 4 * kPBlock - 1) / (4 * kPBlock), c->sm_count));
+            rs.assign((size_t)c->p_ncta + 1, n);
+            rs[0] = 0;
+            int row = 0;
+            for (int b = 1; b < c->p_ncta; ++b) {
+                const int64_t target = total * b / c->p_ncta;
+                while (row < n && (int64_t)c->h_rp[row] + 4 * (int64_t)row < target) ++row;
+                rs[b] = row;
+            }
+            std::vector<int> chunk_ptr((size_t)c->p_ncta + 1, 0), chunk_row;
+            int64_t max_slots = 1;
+            for (int b = 0; b < c->p_ncta; ++b) {
+                chunk_ptr[b] = (int)chunk_row.size();
+                int r = rs[b];
+                while (r < rs[b + 1]) {
+                    chunk_row.push_back(r);
+                    int e = r;
+                    while (e < rs[b + 1] && e - r < kPBlock && (int64_t)c->h_rp[e + 1] - c->h_rp[r] <= cap) ++e;
+                    max_slots = std::max<int64_t>(max_slots, (int64_t)c->h_rp[e] - c->h_rp[r]);
+                    r = e;
+                }
+            }
+            chunk_ptr[c->p_ncta] = (int)chunk_row.size();
+            chunk_row.push_back(n);
+            // chunk_row must give, for chunk q, its end as chunk_row[q + 1]: true inside a CTA; at a CTA boundary
+            // the next CTA's first chunk starts exactly where this one ends (ranges are contiguous)
+            c->d_chunk_ptr = dalloc<int>(chunk_ptr.size());
+            c->d_chunk_row = dalloc<int>(chunk_row.size());
+            CK(cudaMemcpyAsync(c->d_chunk_ptr, chunk_ptr.data(), sizeof(int) * chunk_ptr.size(), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_chunk_row, chunk_row.data(), sizeof(int) * chunk_row.size(), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->slots_smem = (size_t)max_slots * sizeof(double);
+            CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+        }
     }
-    std::vector<int> rs((size_t)c->p_ncta + 1, n);
-    rs[0] = 0;
-    int row = 0;
-    for (int b = 1; b < c->p_ncta; ++b) {
-        const int64_t target = cost[n] * b / c->p_ncta;
-        while (row < n && cost[row] < target) ++row;
-        rs[b] = row;
+    if (c->persist_v != 3) {
+        // CTAs: one per SM at most (cooperative launch => all co-resident); small graphs use fewer so that the
+        // grid barrier stays cheap.
+        int64_t want = ((int64_t)c->n * c->W + kPBlock - 1) / kPBlock;
+        c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>(want, c->sm_count));
+        // contiguous row ranges balanced by the number of 4W-slot passes a row needs plus its length
+        std::vector<int64_t> cost((size_t)n + 1, 0);
+        for (int i = 0; i < n; ++i) {
+            int64_t len = c->h_rp[i + 1] - c->h_rp[i];
+            int64_t passes = std::max<int64_t>(1, (len + 4 * W - 1) / (4 * W));
+            cost[i + 1] = cost[i] + passes * 4 * W + len;
+        }
+        rs.assign((size_t)c->p_ncta + 1, n);
+        rs[0] = 0;
+        int row = 0;
+        for (int b = 1; b < c->p_ncta; ++b) {
+            const int64_t target = cost[n] * b / c->p_ncta;
+            while (row < n && cost[row] < target) ++row;
+            rs[b] = row;
+        }
     }
     c->d_row_start = dalloc<int>(c->p_ncta + 1);
     CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
@@ -473,6 +538,7 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
     CK(cudaStreamSynchronize(c->stream));  // also keeps `coef` alive until the copy is done
     out.lambda2 = c->h_sc->vLv / c->h_sc->vv;
     out.resid = c->h_sc->res1 / (std::sqrt(c->h_sc->vv) * c->lnorm);
+    c->have_prev_v = true;
 }
 
 
@@ -547,8 +613,15 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             if (est * sqrtn < tol * lnorm || exhausted) {
                 *(volatile int*)c->h_stop = 1;
                 CK(cudaStreamSynchronize(c->stream));
+                const int phases_before = phases_done;
                 CK(cudaMemcpy(&phases_done, &c->d_pst->phase, sizeof(int), cudaMemcpyDeviceToHost));
                 c->ab_dirty = std::max(c->ab_dirty, phases_done);
+                if (c->bench_time_iters) {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, c->lz0, c->lz1));
+                    c->lz_kernel_ms += ms;
+                    c->lz_kernel_phases += phases_done - phases_before;
+                }
                 stopped = true;
                 k_conv = k;
                 finalize_ritz(c, k, s, out);
@@ -598,7 +671,7 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     // beta that small would also amplify rounding noise into the next vector.)
     const double brk = std::max(1e-12 * lnorm, 0.25 * tol * lnorm / sqrtn);
 
-    bool use_warm = warm && c->have_v;
+    bool use_warm = warm && c->have_prev_v;
     int total_steps = 0;
     std::vector<double> s;
     for (int restart = 0; restart < 64; ++restart) {
@@ -855,6 +928,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->it0));
         CK(cudaEventCreate(&c->it1));
+        CK(cudaEventCreate(&c->lz0));
+        CK(cudaEventCreate(&c->lz1));
         c->n = n;
         c->ld = ((n + 31) / 32) * 32;
         c->nf = nf;
@@ -868,6 +943,7 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         if (const char* env = getenv("MACB_LANCZOS")) c->persist = (std::string(env) != "graph");
         if (const char* env = getenv("MACB_PERSIST_STREAM")) c->persist_stream = atoi(env) != 0;
         if (const char* env = getenv("MACB_ASYNC")) c->async_rr = atoi(env) != 0;
+        if (const char* env = getenv("MACB_PERSIST_V")) c->persist_v = atoi(env);
 
         c->d_rp = dalloc<int>(n + 1);
         c->d_col = dalloc<int>(c->nnz);
@@ -1158,6 +1234,8 @@ int macb_counters(macb_handle h, int64_t* kernel_launches, int64_t* spmv_launche
 int macb_reset_counters(macb_handle h) {
     if (!h) return MACB_ERR_ARG;
     h->c_launches = h->c_spmv = h->c_steps = h->c_solves = 0;
+    h->lz_kernel_ms = 0.0;
+    h->lz_kernel_phases = 0;
     for (int i = 0; i < MACB_T_COUNT; ++i) h->phase_ms[i] = 0.0;
     return MACB_OK;
 }
@@ -1212,6 +1290,16 @@ extern "C" int macb_debug_ptiming(macb_handle h, long long* out /*[64][ncta][4]*
     });
 }
 #endif
+
+int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double* algo_bytes_per_phase) {
+    if (!h) return MACB_ERR_ARG;
+    if (ms) *ms = h->lz_kernel_ms;
+    if (phases) *phases = h->lz_kernel_phases;
+    // one Lanczos phase = one SpMV + the 32-byte state sector and the 8-byte basis entry per node
+    if (algo_bytes_per_phase)
+        *algo_bytes_per_phase = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n + 40.0 * (double)h->n;
+    return MACB_OK;
+}
 
 int macb_device_sync(macb_handle h) {
     return guarded(h, [&]() {

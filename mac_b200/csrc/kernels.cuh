@@ -586,6 +586,186 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
     }
 }
 
+// ---- K3, slot-parallel form (default) -------------------------------------------------------------------
+// Same state, recurrence, barrier and outputs as k_lanczos_persist, different mapping of work inside a CTA:
+//   pass 1  one thread per SLOT of the CTA's contiguous slot range, four slots in flight per thread, fully
+//           coalesced (col, val) reads; the product  w_s * (u_next[c_s] - k4)  goes to shared memory;
+//   pass 2  one thread per ROW sums its segment from shared memory (no shuffles, no global latency: the row's own
+//           sector was requested before pass 1) and writes the new sector, the basis entry and the partial sums.
+// The gather loop is then exactly the loop tools/micro/gather_mix.cu measures at 0.9 sector/clk/SM -- the
+// divergent-gather ceiling of the LSU/L1TEX path on B200 -- instead of stalling on a per-row reduction after
+// every four gathers.  A CTA's range is cut into chunks of <= kPBlock rows and <= cap slots (shared memory).
+struct LzChunkArgs {
+    const int* chunk_ptr;   // [ncta + 1] chunks of CTA b are chunk_ptr[b] .. chunk_ptr[b+1]
+    const int* chunk_row;   // [nchunks + 1] first row of every chunk (rows of chunk q: chunk_row[q] .. chunk_row[q+1])
+};
+
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, LzChunkArgs ch) {
+    extern __shared__ double prod[];
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double tot[4];
+    __shared__ int stop_sm;
+    const int warp = threadIdx.x >> 5;
+    const int* __restrict__ col = a.col;
+    const double* __restrict__ val = a.val;
+    const int* __restrict__ rp = a.rp;
+    const int q0 = ch.chunk_ptr[blockIdx.x], q1 = ch.chunk_ptr[blockIdx.x + 1];
+
+    int phase = a.st->phase;
+    int cur = a.st->cur;
+    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;
+
+    for (int it = 0; it < a.nphases; ++it, ++phase) {
+        const double* __restrict__ S = a.sect[cur];
+        double* __restrict__ D = a.sect[cur ^ 1];
+        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+        int stop_now = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.stop)
+            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_now) : "l"(a.stop));
+#ifdef MACB_PTIMING
+        long long t_start = clock64();
+#endif
+        for (int q = q0; q < q1; ++q) {
+            const int ra = ch.chunk_row[q], rb = ch.chunk_row[q + 1];
+            const int row = ra + (int)threadIdx.x;
+            const bool has_row = row < rb;
+            double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;
+            if (has_row) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
+            const int sa = rp[ra], sb = rp[rb];
+            for (int i0 = sa + (int)threadIdx.x; i0 < sb; i0 += 4 * kPBlock) {
+                const int i1 = i0 + kPBlock, i2 = i0 + 2 * kPBlock, i3 = i0 + 3 * kPBlock;
+                const bool v1 = i1 < sb, v2 = i2 < sb, v3 = i3 < sb;
+                const int c0 = ld_nc(col + i0), c1 = v1 ? ld_nc(col + i1) : 0, c2 = v2 ? ld_nc(col + i2) : 0,
+                          c3 = v3 ? ld_nc(col + i3) : 0;
+                const double w0 = ld_nc(val + i0), w1 = v1 ? ld_nc(val + i1) : 0.0, w2 = v2 ? ld_nc(val + i2) : 0.0,
+                             w3 = v3 ? ld_nc(val + i3) : 0.0;
+                double z0, u0, g0, z1, u1, g1, z2, u2, g2, z3, u3, g3;
+                ld_sector_if(S + 4 * (size_t)c0, w0 != 0.0, z0, u0, g0);
+                ld_sector_if(S + 4 * (size_t)c1, w1 != 0.0, z1, u1, g1);
+                ld_sector_if(S + 4 * (size_t)c2, w2 != 0.0, z2, u2, g2);
+                ld_sector_if(S + 4 * (size_t)c3, w3 != 0.0, z3, u3, g3);
+                prod[i0 - sa] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+                if (v1) prod[i1 - sa] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+                if (v2) prod[i2 - sa] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+                if (v3) prod[i3 - sa] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
+            }
+            __syncthreads();
+            if (has_row) {
+                const int s0 = rp[row] - sa, s1 = rp[row + 1] - sa;
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = s0;
+                for (; i + 1 < s1; i += 2) {
+                    acc0 += prod[i];
+                    acc1 += prod[i + 1];
+                }
+                if (i < s1) acc0 += prod[i];
+                const double t = fma(k1, oz, fma(k2, ou, k3 * oq));
+                const double un = t + k4;                       // u_phase[row]
+                const double zn = fma(od, t, -(acc0 + acc1));   // (L u_phase)[row]; L 1 = 0 cancels k4
+                st_sector(D + 4 * (size_t)row, zn, un, ou, od);
+                bj[row] = un;
+                p1 = fma(un, zn, p1);
+                p2 += zn;
+                p3 = fma(un, un, p3);
+                p4 += un;
+            }
+            __syncthreads();
+        }
+        // ---- identical to k_lanczos_persist from here: tagged record, counter barrier, fixed-order reduction
+        double v[4] = {p1, p2, p3, p4};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sm[i * kPWarps + warp] = v[i];
+        __syncthreads();
+#ifdef MACB_PTIMING
+        long long t_rows = clock64();
+#endif
+        LzPartRec* recs = a.recs + (size_t)(phase & 1) * a.ncta;
+        const unsigned long long want = (unsigned long long)phase + 1ull;
+        if (warp == 0) {
+            double x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] = sm[i * kPWarps + (threadIdx.x & 31)];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_xor_sync(0xffffffffu, x[i], o);
+            }
+            if (threadIdx.x == 0) {
+                st_sector(recs[blockIdx.x].p, x[0], x[1], x[2], x[3]);
+                if (blockIdx.x == 0) __stcg(&recs[0].pad[0], (unsigned long long)stop_now);
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.st->bar) : "memory");
+                const unsigned int target = (unsigned int)want * (unsigned int)a.ncta;
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&a.st->bar) : "memory");
+                } while ((int)(seen - target) < 0);
+            }
+            __syncwarp();
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            for (int b = (threadIdx.x & 31); b < a.ncta; b += 32) {
+                double r0, r1, r2, r3;
+                ld_sector(recs[b].p, r0, r1, r2, r3);
+                y0 += r0; y1 += r1; y2 += r2; y3 += r3;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, o);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, o);
+                y2 += __shfl_xor_sync(0xffffffffu, y2, o);
+                y3 += __shfl_xor_sync(0xffffffffu, y3, o);
+            }
+            if (threadIdx.x == 0) {
+                tot[0] = y0; tot[1] = y1; tot[2] = y2; tot[3] = y3;
+                stop_sm = (int)__ldcg(&recs[0].pad[0]);
+            }
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        long long t_bar = clock64();
+#endif
+        const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
+        const int stop_all = stop_sm;
+        const double beta = sqrt(P3);
+        const double binv = safe_inv(beta);
+        const double alpha = P1 * binv * binv;
+        const double nk1 = binv, nk2 = -alpha * binv, nk3 = (phase > 0) ? -beta * safe_inv(beta_prev) : 0.0;
+        const double nk4 = -(nk1 * P2 + nk2 * P4 + nk3 * usum_prev) / (double)a.n;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.alpha[phase] = alpha;
+            a.beta[phase] = beta;
+            if (a.ab_host)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(alpha), "d"(beta) : "memory");
+        }
+#ifdef MACB_PTIMING
+        if (threadIdx.x == 0 && a.timing && it < 64) {
+            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            t[0] = t_start; t[1] = t_rows; t[2] = t_bar; t[3] = clock64();
+        }
+#endif
+        k1 = nk1; k2 = nk2; k3 = nk3; k4 = nk4;
+        beta_prev = beta;
+        usum_prev = P4;
+        cur ^= 1;
+        if (stop_all) {
+            ++phase;
+            break;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.st->phase = phase;
+        a.st->cur = cur;
+        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
+        a.st->beta_prev = beta_prev;
+        a.st->usum_prev = usum_prev;
+    }
+}
+
 // sectors for phase 0: (0, src_i, 0, diag_i) with (k1,k2,k3,k4) = (0,1,0,0)  =>  u_0 = src
 __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double* __restrict__ src,
                                                             const double* __restrict__ diag, double* __restrict__ sect0,

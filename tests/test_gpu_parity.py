@@ -167,6 +167,49 @@ def test_warm_start_reaches_the_same_pair():
     mac.close()
 
 
+@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"},
+                                 {"MACB_PERSIST_V": "1", "MACB_ASYNC": "0", "MACB_PERSIST_STREAM": "1"}])
+def test_lanczos_engines_agree(monkeypatch, env):
+    """The default engine (slot-parallel persistent kernel + asynchronous host Rayleigh-Ritz) against the
+    alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel persistent kernel, synchronous batches."""
+    fixed, cand, n = synth.chain_plus_random(4000, 40000, seed=3, weighted=True)
+    x = synth.first_k_init(40000, 8000)
+    ref = MAC(fixed, cand, n)
+    lam0, v0 = ref.fiedler_pair(x)
+    ref.close()
+    for k_, val in env.items():
+        monkeypatch.setenv(k_, val)
+    alt = MAC(fixed, cand, n)
+    lam1, v1 = alt.fiedler_pair(x)
+    assert alt.last_info["converged"]
+    assert abs(lam1 - lam0) <= 1e-10 * lam0
+    assert _same_up_to_sign(v0, v1) < 1e-6
+    w0, u0, _ = alt.frank_wolfe(8000, x, 3, 0.0, 0.0)
+    alt.close()
+    for k_ in env:
+        monkeypatch.delenv(k_)
+    ref = MAC(fixed, cand, n)
+    w1, u1, _ = ref.frank_wolfe(8000, x, 3, 0.0, 0.0)
+    assert np.abs(w0 - w1).max() <= 1e-12 and abs(u0 - u1) <= 1e-7 * abs(u1)
+    ref.close()
+
+
+def test_solves_are_pure_functions_of_their_input():
+    """Same L(x), same start vector => bitwise the same pair, whatever the handle solved before (the check
+    schedule of the asynchronous Rayleigh-Ritz depends on k only, not on timing or history)."""
+    fixed, cand, n = synth.chain_plus_random(3000, 30000, seed=8, weighted=True)
+    xa, xb = synth.first_k_init(30000, 6000), np.full(30000, 0.2)
+    mac = MAC(fixed, cand, n)
+    lam1, v1 = mac.fiedler_pair(xa)
+    mac.fiedler_pair(xb)
+    lam2, v2 = mac.fiedler_pair(xa)
+    other = MAC(fixed, cand, n)
+    lam3, v3 = other.fiedler_pair(xa)
+    assert lam1 == lam2 == lam3 and np.array_equal(v1, v2) and np.array_equal(v1, v3)
+    mac.close()
+    other.close()
+
+
 # ------------------------------------------------------------------------------------------- K4
 def test_gradient_matches_oracle(golden_dir):
     gold = np.load(os.path.join(golden_dir, "er2000.npz"))
@@ -250,6 +293,8 @@ def test_fused_loop_equals_composed_loop():
     k = 2400
     x0 = synth.first_k_init(12000, k)
     w, u, info = mac.frank_wolfe(k, x0, 6, 0.0, 0.0)
+    mac.close()
+    mac = MAC(fixed, cand, n)
     x, ub = x0, np.inf
     fs = []
     for i in range(6):
