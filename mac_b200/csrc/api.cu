@@ -14,6 +14,7 @@
 #include <limits>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "kernels.cuh"
 #include "tridiag.h"
@@ -373,7 +374,10 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.ab_host = async ? c->h_ab : nullptr;
     a.stop = async ? c->h_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
-    if (c->persist_v == 3) {
+    if (c->persist_v == 4) {
+        k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        CK(cudaGetLastError());
+    } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row};
         void* params[] = {&a, &ch};
         CK(cudaLaunchCooperativeKernel((void*)k_lanczos_slots, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
@@ -391,6 +395,17 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
 void setup_persist(macb_ctx* c) {
     const int n = c->n, W = c->W;
     std::vector<int> rs;
+    // small graphs: the whole Lanczos state in one SM's shared memory (k_lanczos_small)
+    const size_t small_bytes = (size_t)32 * n + (size_t)16 * c->nnz;
+    if (c->persist_v == 3 && small_bytes <= (size_t)224 * 1024 && c->nnz <= (int64_t)kSmallSlots * kPBlock &&
+        n <= kSmallRows * kPBlock && !getenv("MACB_NO_SMALL")) {
+        c->persist_v = 4;
+        c->p_ncta = 1;
+        c->slots_smem = small_bytes;
+        CK(cudaFuncSetAttribute((const void*)k_lanczos_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+        rs.assign(2, n);
+        rs[0] = 0;
+    }
     if (c->persist_v == 3) {
         // slot-parallel kernel: CTAs sized by work (one slot = 1, one row = 4), chunks of <= kPBlock rows and
         // <= cap slots so that a chunk's products fit in shared memory
@@ -436,7 +451,7 @@ void setup_persist(macb_ctx* c) {
             CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
         }
     }
-    if (c->persist_v != 3) {
+    if (c->persist_v != 3 && c->persist_v != 4) {
         // CTAs: one per SM at most (cooperative launch => all co-resident); small graphs use fewer so that the
         // grid barrier stays cheap.
         int64_t want = ((int64_t)c->n * c->W + kPBlock - 1) / kPBlock;
@@ -544,7 +559,7 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
 
 // Check points of the asynchronous Rayleigh-Ritz: a function of k alone, so that the step count at which a solve
 // stops -- and with it the result, to the last bit -- does not depend on host/device timing.
-inline int next_check(int k) { return k + std::max(16, 16 * (k / 256)); }
+inline int next_check(int k) { return k + std::max(16, 16 * (k / 128)); }
 
 // One Lanczos cycle on the persistent engine with the host Rayleigh-Ritz running concurrently with the kernel.
 // Returns: 1 converged (result in `out`, vector in d_v), 0 cycle exhausted without convergence (best Ritz vector
@@ -554,6 +569,11 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
     const int n = c->n;
     const double sqrtn = std::sqrt((double)n), lnorm = c->lnorm;
     const double nan = std::numeric_limits<double>::quiet_NaN();
+    static const bool trace = getenv("MACB_TRACE") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - T0).count(); };
+    double t_wait = 0.0, t_rr = 0.0;
+    int n_checks = 0;
     volatile double* ab = c->h_ab;
     int phases_done = 0;   // phases the device has completed in earlier launches of this cycle
     int k_next = std::min(16, k_limit);
@@ -579,6 +599,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             // wait for beta[k_next] (phase k_next) or for the kernel to end
             const int need = std::min(k_next, k_limit);
             bool kernel_done = false;
+            const double tw0 = us();
             while (std::isnan(ab[2 * need + 1])) {
                 if (cudaStreamQuery(c->stream) != cudaErrorNotReady) {
                     kernel_done = true;
@@ -589,6 +610,8 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 CK(cudaStreamSynchronize(c->stream));  // surfaces launch/runtime errors
                 if (std::isnan(ab[2 * need + 1])) throw ArgFail{"macb_fiedler: Lanczos kernel ended early", MACB_ERR_STATE};
             }
+            const double tw1 = us();
+            t_wait += tw1 - tw0;
             for (int j = k_seen; j <= need; ++j) {
                 c->h_alpha[j] = ab[2 * j];
                 c->h_beta[j] = ab[2 * j + 1];
@@ -610,9 +633,15 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             theta_prev = theta;
             const double est = std::fabs(c->h_beta[k]) * std::fabs(s[k - 1]);
             const bool exhausted = invariant || need >= k_limit;
+            t_rr += us() - tw1;
+            ++n_checks;
             if (est * sqrtn < tol * lnorm || exhausted) {
                 *(volatile int*)c->h_stop = 1;
+                const double ts0 = us();
                 CK(cudaStreamSynchronize(c->stream));
+                if (trace)
+                    fprintf(stderr, "[macb] k=%d checks=%d wait=%.0fus rr=%.0fus stop->sync=%.0fus t=%.0fus\n", k, n_checks, t_wait, t_rr,
+                            us() - ts0, us());
                 const int phases_before = phases_done;
                 CK(cudaMemcpy(&phases_done, &c->d_pst->phase, sizeof(int), cudaMemcpyDeviceToHost));
                 c->ab_dirty = std::max(c->ab_dirty, phases_done);
@@ -625,6 +654,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 stopped = true;
                 k_conv = k;
                 finalize_ritz(c, k, s, out);
+                if (trace) fprintf(stderr, "[macb] phases=%d finalize done t=%.0fus resid=%.2e\n", phases_done, us(), out.resid);
                 if (out.resid < tol) {
                     total_steps += phases_done;
                     c->c_steps += phases_done;

@@ -55,6 +55,25 @@ __device__ __forceinline__ int ld_stream(const int* p) {
 
 __device__ __forceinline__ double safe_inv(double b) { return (b > 1e-290) ? 1.0 / b : 0.0; }
 
+// Coefficients of the next Lanczos vector from the four global sums (p1 = u.z, p2 = sum z, p3 = u.u, p4 = sum u).
+// The chain is on the critical path of every step on every CTA, so it avoids double-precision divide and sqrt
+// (each a ~100-instruction sequence): one rsqrt, then multiplications only.
+struct LzCoef {
+    double alpha, beta, binv, k1, k2, k3, k4;
+};
+__device__ __forceinline__ LzCoef lz_coefficients(double P1, double P2, double P3, double P4, double binv_prev,
+                                                  double usum_prev, double inv_n) {
+    LzCoef c;
+    c.binv = (P3 > 1e-290) ? rsqrt(P3) : 0.0;
+    c.beta = P3 * c.binv;
+    c.alpha = P1 * c.binv * c.binv;
+    c.k1 = c.binv;
+    c.k2 = -c.alpha * c.binv;
+    c.k3 = -c.beta * binv_prev;            // binv_prev = 0 on the first step
+    c.k4 = -(c.k1 * P2 + c.k2 * P4 + c.k3 * usum_prev) * inv_n;
+    return c;
+}
+
 // ---- block / grid reductions (fixed tree => bitwise reproducible for a fixed grid) ---------------
 template <int NV, bool MAXOP = false>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double* sm /*[NV * kWarpsPerBlock]*/) {
@@ -408,7 +427,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
     int phase = a.st->phase;
     int cur = a.st->cur;
     double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
-    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed step
+    const double inv_n = 1.0 / (double)a.n;
 
     for (int it = 0; it < a.nphases; ++it, ++phase) {
         const double* __restrict__ S = a.sect[cur];
@@ -551,11 +571,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
 #endif
         const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
         const int stop_all = stop_sm;
-        const double beta = sqrt(P3);
-        const double binv = safe_inv(beta);
-        const double alpha = P1 * binv * binv;
-        const double nk1 = binv, nk2 = -alpha * binv, nk3 = (phase > 0) ? -beta * safe_inv(beta_prev) : 0.0;
-        const double nk4 = -(nk1 * P2 + nk2 * P4 + nk3 * usum_prev) / (double)a.n;
+        const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
+        const double alpha = cf.alpha, beta = cf.beta;
+        const double nk1 = cf.k1, nk2 = cf.k2, nk3 = cf.k3, nk4 = cf.k4;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             a.alpha[phase] = alpha;
             a.beta[phase] = beta;
@@ -569,7 +587,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
         }
 #endif
         k1 = nk1; k2 = nk2; k3 = nk3; k4 = nk4;
-        beta_prev = beta;
+        beta_prev = cf.binv;   // (holds 1/beta of the completed step)
         usum_prev = P4;
         cur ^= 1;
         if (stop_all) {
@@ -614,7 +632,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
     int phase = a.st->phase;
     int cur = a.st->cur;
     double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
-    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed step
+    const double inv_n = 1.0 / (double)a.n;
 
     for (int it = 0; it < a.nphases; ++it, ++phase) {
         const double* __restrict__ S = a.sect[cur];
@@ -731,11 +750,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
 #endif
         const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
         const int stop_all = stop_sm;
-        const double beta = sqrt(P3);
-        const double binv = safe_inv(beta);
-        const double alpha = P1 * binv * binv;
-        const double nk1 = binv, nk2 = -alpha * binv, nk3 = (phase > 0) ? -beta * safe_inv(beta_prev) : 0.0;
-        const double nk4 = -(nk1 * P2 + nk2 * P4 + nk3 * usum_prev) / (double)a.n;
+        const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
+        const double alpha = cf.alpha, beta = cf.beta;
+        const double nk1 = cf.k1, nk2 = cf.k2, nk3 = cf.k3, nk4 = cf.k4;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             a.alpha[phase] = alpha;
             a.beta[phase] = beta;
@@ -749,7 +766,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
         }
 #endif
         k1 = nk1; k2 = nk2; k3 = nk3; k4 = nk4;
-        beta_prev = beta;
+        beta_prev = cf.binv;   // (holds 1/beta of the completed step)
         usum_prev = P4;
         cur ^= 1;
         if (stop_all) {
@@ -760,6 +777,178 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.st->phase = phase;
         a.st->cur = cur;
+        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
+        a.st->beta_prev = beta_prev;
+        a.st->usum_prev = usum_prev;
+    }
+}
+
+// ---- K3, single-CTA form for small graphs (pose graphs with n up to 3072 nodes, 12288 slots) -------------
+// When 24 n + 16 nnz bytes fit in one SM's shared memory the whole problem lives on that SM: (z, u, u') per
+// node, the edge weights and the per-slot products in shared memory; column indices, row extents and the
+// diagonal in registers (each thread owns slots tid + 1024 j and rows tid + 1024 r for the whole kernel).  A step
+// is two block-level passes and __syncthreads -- no grid barrier and no global load at all on the critical
+// path.  Same recurrence and outputs (basis, alpha, beta, streamed alpha/beta, stop flag) as k_lanczos_slots.
+constexpr int kSmallSlots = 12;   // slots per thread  => nnz <= 12 * 1024
+constexpr int kSmallRows = 3;     // rows per thread   => n   <=  3 * 1024
+
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, const double* __restrict__ diag) {
+    extern __shared__ double smem_small[];
+    const int n = a.n;
+    const int nnz = a.rp[n];
+    double* __restrict__ sec = smem_small;                       // [3 n]
+    double* __restrict__ prod = sec + 3 * (size_t)n;             // [nnz]
+    double* __restrict__ wts = prod + nnz;                       // [nnz]
+    double* __restrict__ tvec = wts + nnz;                       // [n]  u_next - k4, materialised once per phase
+    __shared__ double ks[4];
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double tot[4];
+    __shared__ int stop_small;
+    if (threadIdx.x == 0) stop_small = 0;
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+
+    int pc[kSmallSlots];
+#pragma unroll
+    for (int j = 0; j < kSmallSlots; ++j) {
+        const int i = threadIdx.x + kPBlock * j;
+        pc[j] = (i < nnz) ? a.col[i] : 0;
+        if (i < nnz) wts[i] = a.val[i];
+    }
+    int rs0[kSmallRows], rs1[kSmallRows];
+    double rd[kSmallRows];
+#pragma unroll
+    for (int r = 0; r < kSmallRows; ++r) {
+        const int row = threadIdx.x + kPBlock * r;
+        rs0[r] = (row < n) ? a.rp[row] : 0;
+        rs1[r] = (row < n) ? a.rp[row + 1] : 0;
+        rd[r] = (row < n) ? diag[row] : 0.0;
+    }
+    int phase = a.st->phase;
+    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed step
+    const double inv_n = 1.0 / (double)a.n;
+    double* __restrict__ G = a.sect[0];
+    for (int i = threadIdx.x; i < n; i += kPBlock) {
+        double z, u, q, d;
+        ld_sector(G + 4 * (size_t)i, z, u, q, d);
+        sec[3 * i] = z;
+        sec[3 * i + 1] = u;
+        sec[3 * i + 2] = q;
+    }
+    __syncthreads();
+    int stop_probe = 0;
+    bool stop_all = false;
+    double pend_alpha = 0.0, pend_beta = 0.0;
+#ifdef MACB_PTIMING
+    const long long t_begin = clock64();
+    const int phase_begin = phase;
+    long long t_p1 = 0, t_p2 = 0, t_red = 0;
+#endif
+
+    for (int it = 0; it < a.nphases && !stop_all; ++it, ++phase) {
+#ifdef MACB_PTIMING
+        const long long tt0 = clock64();
+#endif
+        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
+        // host stop flag: requested every 8th phase, looked at 7 phases later (a host-memory load takes microseconds)
+        if (threadIdx.x == 0 && a.stop && (it & 7) == 0)
+            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_probe) : "l"(a.stop));
+        // one shared-memory gather per slot instead of three: shared-memory bandwidth (128 B/clk) is what bounds
+        // a single-SM step
+#pragma unroll
+        for (int r = 0; r < kSmallRows; ++r) {
+            const int row = threadIdx.x + kPBlock * r;
+            if (row < n) tvec[row] = fma(k1, sec[3 * row], fma(k2, sec[3 * row + 1], k3 * sec[3 * row + 2]));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSmallSlots; ++j) {
+            const int i = threadIdx.x + kPBlock * j;
+            if (i < nnz) {
+                const double w = wts[i];
+                prod[i] = (w != 0.0) ? w * tvec[pc[j]] : 0.0;
+            }
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        const long long tt1 = clock64();
+#endif
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kSmallRows; ++r) {
+            const int row = threadIdx.x + kPBlock * r;
+            if (row < n) {
+                double acc = 0.0;
+                for (int i = rs0[r]; i < rs1[r]; ++i) acc += prod[i];
+                const double u = sec[3 * row + 1];
+                const double t = tvec[row];
+                const double un = t + k4;
+                const double zn = fma(rd[r], t, -acc);
+                sec[3 * row] = zn;
+                sec[3 * row + 1] = un;
+                sec[3 * row + 2] = u;
+                bj[row] = un;
+                p1 = fma(un, zn, p1);
+                p2 += zn;
+                p3 = fma(un, un, p3);
+                p4 += un;
+            }
+        }
+#ifdef MACB_PTIMING
+        const long long tt2 = clock64();
+#endif
+        double v[4] = {p1, p2, p3, p4};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if (wl == 0)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sm[i * kPWarps + warp] = v[i];
+        __syncthreads();
+        if (warp < 4) {
+            double x = sm[warp * kPWarps + wl];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (wl == 0) tot[warp] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {   // one thread does the scalar algebra (double sqrt / divide are ~100-instruction sequences)
+            const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
+            const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
+            ks[0] = cf.k1; ks[1] = cf.k2; ks[2] = cf.k3; ks[3] = cf.k4;
+            beta_prev = cf.binv;
+            usum_prev = P4;
+            pend_alpha = cf.alpha;
+            pend_beta = cf.beta;
+            if (a.stop && (it & 7) == 7) stop_small = stop_probe;
+        }
+        __syncthreads();
+        k1 = ks[0]; k2 = ks[1]; k3 = ks[2]; k4 = ks[3];
+        if (threadIdx.x == 0) {   // after the barrier: the other warps are already in the next step
+            a.alpha[phase] = pend_alpha;
+            a.beta[phase] = pend_beta;
+            if (a.ab_host)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(pend_alpha), "d"(pend_beta) : "memory");
+        }
+        stop_all = (stop_small != 0);
+#ifdef MACB_PTIMING
+        { const long long tt3 = clock64(); t_p1 += tt1 - tt0; t_p2 += tt2 - tt1; t_red += tt3 - tt2; }
+#endif
+        // no barrier needed here: the next pass 1 only reads `sec`, which every thread finished writing before the
+        // two barriers above; `tot` / `sm` are rewritten only after the next pass-1 barrier
+    }
+#ifdef MACB_PTIMING
+    if (threadIdx.x == 0 && a.timing) {
+        a.timing[0] = clock64() - t_begin; a.timing[1] = phase - phase_begin; a.timing[2] = t_p1; a.timing[3] = t_p2; a.timing[4] = t_red;
+    }
+#endif
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kPBlock)
+        st_sector(G + 4 * (size_t)i, sec[3 * i], sec[3 * i + 1], sec[3 * i + 2], diag[i]);
+    if (threadIdx.x == 0) {
+        a.st->phase = phase;
+        a.st->cur = 0;
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = beta_prev;
         a.st->usum_prev = usum_prev;

@@ -11,6 +11,9 @@
 #include <cfloat>
 #include <cmath>
 #include <limits>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace macb {
 
@@ -27,6 +30,50 @@ inline bool has_eig_below(const double* a, const double* b2, int k, double x, do
         if (q < 0.0) return true;
     }
     return false;
+}
+
+#if defined(__x86_64__)
+// Eight Sturm recurrences at once (two AVX2 vectors): neg[j] != 0 <=> T - x[j] I has a negative pivot.
+__attribute__((target("avx2"))) void sturm8_avx2(const double* a, const double* b2, int k, const double* x, double pivmin,
+                                                 double* neg) {
+    const __m256d pm = _mm256_set1_pd(pivmin), npm = _mm256_set1_pd(-pivmin), zero = _mm256_setzero_pd();
+    const __m256d absmask = _mm256_castsi256_pd(_mm256_set1_epi64x(0x7fffffffffffffffLL));
+    const __m256d x0 = _mm256_loadu_pd(x), x1 = _mm256_loadu_pd(x + 4);
+    __m256d q0 = _mm256_sub_pd(_mm256_set1_pd(a[0]), x0), q1 = _mm256_sub_pd(_mm256_set1_pd(a[0]), x1);
+    q0 = _mm256_blendv_pd(q0, npm, _mm256_cmp_pd(_mm256_and_pd(q0, absmask), pm, _CMP_LT_OQ));
+    q1 = _mm256_blendv_pd(q1, npm, _mm256_cmp_pd(_mm256_and_pd(q1, absmask), pm, _CMP_LT_OQ));
+    __m256d n0 = _mm256_cmp_pd(q0, zero, _CMP_LT_OQ), n1 = _mm256_cmp_pd(q1, zero, _CMP_LT_OQ);
+    for (int i = 1; i < k; ++i) {
+        const __m256d ai = _mm256_set1_pd(a[i]), bi = _mm256_set1_pd(b2[i]);
+        __m256d t0 = _mm256_sub_pd(_mm256_sub_pd(ai, x0), _mm256_div_pd(bi, q0));
+        __m256d t1 = _mm256_sub_pd(_mm256_sub_pd(ai, x1), _mm256_div_pd(bi, q1));
+        t0 = _mm256_blendv_pd(t0, npm, _mm256_cmp_pd(_mm256_and_pd(t0, absmask), pm, _CMP_LT_OQ));
+        t1 = _mm256_blendv_pd(t1, npm, _mm256_cmp_pd(_mm256_and_pd(t1, absmask), pm, _CMP_LT_OQ));
+        n0 = _mm256_or_pd(n0, _mm256_cmp_pd(t0, zero, _CMP_LT_OQ));
+        n1 = _mm256_or_pd(n1, _mm256_cmp_pd(t1, zero, _CMP_LT_OQ));
+        q0 = t0;
+        q1 = t1;
+    }
+    alignas(32) double m[8];
+    _mm256_store_pd(m, n0);
+    _mm256_store_pd(m + 4, n1);
+    for (int j = 0; j < 8; ++j) {
+        unsigned long long bits;
+        __builtin_memcpy(&bits, &m[j], 8);
+        neg[j] = bits ? 1.0 : 0.0;
+    }
+}
+#endif
+
+void sturm8(const double* a, const double* b2, int k, const double* x, double pivmin, double* neg) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        sturm8_avx2(a, b2, k, x, pivmin, neg);
+        return;
+    }
+#endif
+    for (int j = 0; j < 8; ++j) neg[j] = has_eig_below(a, b2, k, x[j], pivmin) ? 1.0 : 0.0;
 }
 
 }  // namespace
@@ -80,22 +127,89 @@ double tridiag_smallest_value(const double* a, const double* b, int k, double hi
             }
         }
     }
-    for (int it = 0; it < 200; ++it) {
-        double mid = 0.5 * (lo + hi);
-        if (!(hi - lo > 2.0 * DBL_EPSILON * std::max(std::fabs(lo), std::fabs(hi)) + 2.0 * pivmin)) break;
-        if (mid <= lo || mid >= hi) break;
-        if (has_eig_below(a, b2.data(), k, mid, pivmin))
-            hi = mid;
-        else
-            lo = mid;
+    // Multisection: kSec interior shifts per sweep, evaluated together (the division chain of one Sturm
+    // recurrence is latency-bound; eight independent chains fill the divider and vectorise), so one sweep
+    // shrinks the bracket 9x instead of 2x.
+    constexpr int kSec = 8;   // sturm8 evaluates exactly eight shifts
+    for (int it = 0; it < 80; ++it) {
+        const double width = hi - lo;
+        if (!(width > 2.0 * DBL_EPSILON * std::max(std::fabs(lo), std::fabs(hi)) + 2.0 * pivmin)) break;
+        alignas(64) double x[kSec], neg[kSec];   // neg[j] > 0 <=> chain j has seen a negative pivot
+        for (int j = 0; j < kSec; ++j) {
+            x[j] = lo + width * (double)(j + 1) / (double)(kSec + 1);
+            neg[j] = 0.0;
+        }
+        if (!(x[0] > lo) || !(x[kSec - 1] < hi)) {  // bracket at rounding resolution: finish with plain bisection
+            double mid = 0.5 * (lo + hi);
+            if (mid <= lo || mid >= hi) break;
+            if (has_eig_below(a, b2.data(), k, mid, pivmin)) hi = mid; else lo = mid;
+            continue;
+        }
+        sturm8(a, b2.data(), k, x, pivmin, neg);
+        // eigenvalue lies between the last shift with no negative pivot and the first with one
+        int first_neg = kSec;
+        for (int j = kSec - 1; j >= 0; --j)
+            if (neg[j] > 0.0) first_neg = j;
+        const double new_lo = (first_neg == 0) ? lo : x[first_neg - 1];
+        const double new_hi = (first_neg == kSec) ? hi : x[first_neg];
+        lo = new_lo;
+        hi = new_hi;
     }
     return 0.5 * (lo + hi);
 }
+
+namespace {
+
+double tridiag_residual(const double* a, const double* b, int k, double theta, const double* s) {
+    double rr = 0.0;
+    for (int i = 0; i < k; ++i) {
+        double t = (a[i] - theta) * s[i];
+        if (i > 0) t += b[i] * s[i - 1];
+        if (i + 1 < k) t += b[i + 1] * s[i + 1];
+        rr += t * t;
+    }
+    return std::sqrt(rr);
+}
+
+// Eigenvector for the SMALLEST eigenvalue by the forward pivot recurrence alone: theta <= lambda_min(T_j) for
+// every leading block (interlacing), so T_j - theta I is positive (semi)definite, the pivots q_i are positive
+// and s_{i+1} = -(q_i / b_{i+1}) s_i is the stable LDL^T forward substitution.  One pass, one division per row.
+bool forward_vector(const double* a, const double* b, int k, double theta, double tnorm, double* s) {
+    const double tiny = std::max(DBL_EPSILON * tnorm, DBL_MIN * 1e8);
+    double q = a[0] - theta;
+    s[0] = 1.0;
+    double ss = 1.0;
+    for (int i = 0; i + 1 < k; ++i) {
+        const double bn = b[i + 1];
+        if (!(std::fabs(bn) > 0.0)) return false;
+        double si = -(q / bn) * s[i];
+        if (!(std::fabs(si) < 1e140)) return false;   // growth: leave it to the twisted factorisation
+        s[i + 1] = si;
+        ss += si * si;
+        if (std::fabs(q) < tiny) q = (q < 0 ? -tiny : tiny);
+        q = (a[i + 1] - theta) - bn * bn / q;
+    }
+    if (!(ss > 0.0) || !std::isfinite(ss)) return false;
+    const double inv = 1.0 / std::sqrt(ss);
+    for (int i = 0; i < k; ++i) s[i] *= inv;
+    return true;
+}
+
+}  // namespace
 
 double tridiag_vector(const double* a, const double* b, int k, double theta, double* s) {
     if (k == 1) {
         s[0] = 1.0;
         return std::fabs(a[0] - theta);
+    }
+    {
+        double tn = 0.0;
+        for (int i = 0; i < k; ++i)
+            tn = std::max(tn, std::fabs(a[i]) + (i > 0 ? std::fabs(b[i]) : 0.0) + (i + 1 < k ? std::fabs(b[i + 1]) : 0.0));
+        if (forward_vector(a, b, k, theta, tn, s)) {
+            const double r = tridiag_residual(a, b, k, theta, s);
+            if (r <= 1e-11 * tn) return r;
+        }
     }
     double tnorm = 0.0;
     for (int i = 0; i < k; ++i)
@@ -156,15 +270,7 @@ double tridiag_vector(const double* a, const double* b, int k, double theta, dou
     }
     double inv = 1.0 / std::sqrt(ss);
     for (int i = 0; i < k; ++i) s[i] *= inv;
-    // residual
-    double rr = 0.0;
-    for (int i = 0; i < k; ++i) {
-        double t = (a[i] - theta) * s[i];
-        if (i > 0) t += b[i] * s[i - 1];
-        if (i + 1 < k) t += b[i + 1] * s[i + 1];
-        rr += t * t;
-    }
-    return std::sqrt(rr);
+    return tridiag_residual(a, b, k, theta, s);
 }
 
 }  // namespace macb
