@@ -94,6 +94,14 @@ int macb_topk(macb_handle h, int64_t k, double* s);
 /* Same LP oracle for an arbitrary host vector g[m] (no handle state involved). */
 int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s);
 
+/* Replaces round_nearest(w, k, weights=kappa, break_ties_decimal_tol=decimals) (rounding.py:30-42, called at
+ * mac.py:207): the k largest entries in the lexicographic order (numpy.round(w, decimals), kappa); entries equal in
+ * both keys are taken lowest index first (numpy's argpartition leaves that order unspecified).  w[m] in,
+ * rounded[m] in {0,1} out.  The _dense form takes the tie-break weights explicitly and needs no handle. */
+int macb_round_nearest(macb_handle h, const double* w, int64_t k, int decimals, double* rounded);
+int macb_round_nearest_dense(int device, const double* w, const double* weights, int64_t m, int64_t k, int decimals,
+                             double* rounded);
+
 /* ---- whole Frank-Wolfe loop ------------------------------------------------------------------- */
 
 /* Replaces frank_wolfe (frankwolfe.py:10-79) specialised as MAC.solve calls it (mac.py:186-200):

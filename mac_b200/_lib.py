@@ -61,6 +61,8 @@ def lib():
     _sig(L.macb_gradient, [H, _dp])
     _sig(L.macb_topk, [H, C.c_int64, _dp])
     _sig(L.macb_topk_dense, [C.c_int, _dp, C.c_int64, C.c_int64, _dp])
+    _sig(L.macb_round_nearest, [H, _dp, C.c_int64, C.c_int, _dp])
+    _sig(L.macb_round_nearest_dense, [C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp])
     _sig(L.macb_fw_run, [H, C.c_int64, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                          _dp, _dp, C.POINTER(C.c_int), _dp, _dp])
     _sig(L.macb_counters, [H, _lp, _lp, _lp, _lp, _dp])
@@ -180,6 +182,13 @@ class Handle:
         self._check(self._L.macb_topk(self._h, int(k), _p(s, _dp) if want else None), "macb_topk")
         return s
 
+    def round_nearest(self, w, k, decimals=10):
+        w = _f64(w)
+        assert w.shape == (self.m,)
+        out = np.empty(self.m)
+        self._check(self._L.macb_round_nearest(self._h, _p(w, _dp), int(k), int(decimals), _p(out, _dp)), "macb_round_nearest")
+        return out
+
     # -- whole loop
     def fw_run(self, k, x_init, max_iters, rel_gap_tol, grad_norm_tol, fiedler_tol=1e-8, min_sel_tol=1e-10,
                fiedler_max_steps=0, warm=False):
@@ -253,6 +262,18 @@ def topk_dense(g, k, device=-1):
     if rc != MACB_OK:
         raise MacbError(f"macb_topk_dense failed ({rc}): {L.macb_last_error(None).decode()}")
     return s
+
+
+def round_nearest_dense(w, weights, k, decimals, device=-1):
+    """Tie-broken nearest rounding (rounding.py:30-42) on the device for arbitrary host vectors."""
+    L = lib()
+    w, weights = _f64(w), _f64(weights)
+    assert w.shape == weights.shape
+    out = np.empty_like(w)
+    rc = L.macb_round_nearest_dense(int(device), _p(w, _dp), _p(weights, _dp), w.size, int(k), int(decimals), _p(out, _dp))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_round_nearest_dense failed ({rc}): {L.macb_last_error(None).decode()}")
+    return out
 
 
 def tridiag_smallest(a, b):

@@ -106,6 +106,8 @@ struct macb_ctx {
     SelState* d_sel_state = nullptr;
     unsigned int* d_blockcnt = nullptr;
     SelState* h_sel_state = nullptr;  // pinned
+    SelState* d_sel_state2 = nullptr;
+    double *d_tmp_m2 = nullptr, *d_tmp_m3 = nullptr;
     cudaGraphExec_t sel_graph = nullptr;
 
     void* d_flush = nullptr;
@@ -239,7 +241,7 @@ void free_all(macb_ctx* c) {
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
-                     c->d_sel_state, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
+                     c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
                      c->d_pst, c->d_ptiming};
     for (void* p : dptrs)
         if (p) cudaFree(p);
@@ -838,33 +840,34 @@ void launch_gradient(macb_ctx* c) {
 }
 
 // radix-select passes over `g` (device, length m) + selection mask into `sel`; dual term into sc
-void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel) {
+void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel, SelState* st = nullptr) {
+    if (!st) st = c->d_sel_state;
     PhaseTimer pt(c, MACB_T_TOPK);
     const int64_t m = c->m;
     const int grid = c->grid_for(m);
-    k_sel_init<<<1, kBlock, 0, c->stream>>>(c->d_sel_state, (long long)k);
+    k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
     c->c_launches++;
     if (k > 0) {
         for (int shift = 56; shift >= 0; shift -= 8) {
-            k_sel_hist<<<grid, kBlock, 0, c->stream>>>(m, g, c->d_sel_state, shift);
-            k_sel_pick<<<1, kBlock, 0, c->stream>>>(c->d_sel_state, shift);
+            k_sel_hist<<<grid, kBlock, 0, c->stream>>>(m, g, st, shift);
+            k_sel_pick<<<1, kBlock, 0, c->stream>>>(st, shift);
         }
         c->c_launches += 16;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_sel_state, c->d_sel_state, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_sel_state, st, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     int64_t chunk = (m + grid - 1) / grid;
     chunk = ((chunk + kBlock - 1) / kBlock) * kBlock;
     const int nblocks = (int)((m + chunk - 1) / chunk);
     const bool ranked = k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining;
     if (ranked) {
-        k_sel_tie_count<<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, c->d_sel_state, c->d_blockcnt);
+        k_sel_tie_count<<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, st, c->d_blockcnt);
         k_sel_tie_scan<<<1, 32, 0, c->stream>>>(nblocks, c->d_blockcnt);
-        k_sel_apply<true><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, c->d_sel_state, c->d_blockcnt, sel, c->d_sc, c->ws());
+        k_sel_apply<true><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, st, c->d_blockcnt, sel, c->d_sc, c->ws());
         c->c_launches += 3;
     } else {
-        k_sel_apply<false><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, c->d_sel_state, c->d_blockcnt, sel, c->d_sc, c->ws());
+        k_sel_apply<false><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, st, c->d_blockcnt, sel, c->d_sc, c->ws());
         c->c_launches += 1;
     }
     CK(cudaGetLastError());
@@ -1137,6 +1140,65 @@ int macb_topk(macb_handle h, int64_t k, double* s) {
         CK(cudaStreamSynchronize(h->stream));
         return (int)MACB_OK;
     });
+}
+
+// Tie-broken nearest rounding on the device.  Stage 1: radix select on t = round(w, decimals).  If more elements
+// tie with the k-th value of t than are still needed, stage 2 selects among exactly those by edge weight.
+static void round_nearest_device(macb_ctx* h, int64_t k, int decimals, double* out_host) {
+    const int64_t m = h->m;
+    if (!h->d_tmp_m2) {
+        h->d_tmp_m2 = dalloc<double>(m);
+        h->d_tmp_m3 = dalloc<double>(m);
+        h->d_sel_state2 = dalloc<SelState>(1);
+    }
+    const int grid = h->grid_for(m);
+    double p10 = 1.0;
+    for (int i = 0; i < decimals; ++i) p10 *= 10.0;
+    // d_tmp_m holds w (uploaded by the caller); t -> d_tmp_m2
+    k_round_decimals<<<grid, kBlock, 0, h->stream>>>(m, h->d_tmp_m, p10, h->d_tmp_m2);
+    launch_topk(h, h->d_tmp_m2, h->d_x, k, h->d_sel, h->d_sel_state);   // leaves the k-th key of t in d_sel_state
+    const bool ties = k > 0 && h->h_sel_state->eq_total != h->h_sel_state->remaining;
+    if (!ties) {
+        k_mask_to_double<<<grid, kBlock, 0, h->stream>>>(m, h->d_sel, h->d_tmp_m3);
+        h->c_launches += 2;
+    } else {
+        const int64_t need = h->h_sel_state->remaining;
+        k_tie_keys<<<grid, kBlock, 0, h->stream>>>(m, h->d_tmp_m2, h->d_kappa, h->d_sel_state, h->d_tmp_m3);
+        launch_topk(h, h->d_tmp_m3, h->d_x, need, h->d_sel, h->d_sel_state2);
+        k_round_merge<<<grid, kBlock, 0, h->stream>>>(m, h->d_tmp_m2, h->d_sel_state, h->d_sel, h->d_tmp_m3);
+        h->c_launches += 3;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, h->d_tmp_m3, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_sel = false;
+}
+
+int macb_round_nearest(macb_handle h, const double* w, int64_t k, int decimals, double* rounded) {
+    return guarded(h, [&]() {
+        if (!w || !rounded) throw ArgFail{"macb_round_nearest: NULL buffer", MACB_ERR_ARG};
+        if (k < 0 || k > h->m || decimals < 0 || decimals > 15) throw ArgFail{"macb_round_nearest: bad k / decimals", MACB_ERR_ARG};
+        if (h->m == 0) return (int)MACB_OK;
+        CK(cudaMemcpyAsync(h->d_tmp_m, w, sizeof(double) * h->m, cudaMemcpyHostToDevice, h->stream));
+        round_nearest_device(h, k, decimals, rounded);
+        return (int)MACB_OK;
+    });
+}
+
+int macb_round_nearest_dense(int device, const double* w, const double* weights, int64_t m, int64_t k, int decimals,
+                             double* rounded) {
+    if (!w || !weights || !rounded || m < 1 || k < 0 || k > m) {
+        g_create_error = "macb_round_nearest_dense: bad arguments";
+        return MACB_ERR_ARG;
+    }
+    std::vector<int32_t> zi((size_t)m, 0);
+    macb_handle h = nullptr;
+    int rc = macb_create(1, 0, nullptr, nullptr, nullptr, m, zi.data(), zi.data(), weights, device, &h);
+    if (rc != MACB_OK) return rc;
+    rc = macb_round_nearest(h, w, k, decimals, rounded);
+    if (rc != MACB_OK) g_create_error = h->err;
+    macb_destroy(h);
+    return rc;
 }
 
 int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s) {

@@ -1056,6 +1056,7 @@ struct SelState {
 
 __device__ __forceinline__ unsigned long long order_key(double g) {
     unsigned long long b = (unsigned long long)__double_as_longlong(g);
+    if (b == 0x8000000000000000ull) b = 0ull;   // -0.0 and +0.0 compare equal (numpy / IEEE), so they share a key
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
@@ -1218,6 +1219,30 @@ __global__ void __launch_bounds__(kBlock) k_fw_update(int64_t m, double gamma, c
         x[e] = xn;
         ew_cand[e] = (xn > tol) ? xn * kappa[e] : 0.0;
     }
+}
+
+// ---- tie-broken nearest rounding (rounding.py:30-42) -----------------------------------------------------
+// t = numpy.round(w, decimals): rint(w * 10^d) / 10^d, each operation rounded separately like numpy's C loop.
+__global__ void __launch_bounds__(kBlock) k_round_decimals(int64_t m, const double* __restrict__ w, double p10,
+                                                           double* __restrict__ t) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x)
+        t[e] = __ddiv_rn(rint(__dmul_rn(w[e], p10)), p10);
+}
+
+// second key of the lexicographic order: the edge weight where the first key ties with the k-th value, -inf elsewhere
+__global__ void __launch_bounds__(kBlock) k_tie_keys(int64_t m, const double* __restrict__ t, const double* __restrict__ kappa,
+                                                     const SelState* st, double* __restrict__ out) {
+    const unsigned long long kth = st->prefix;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = (order_key(t[e]) == kth) ? kappa[e] : -INFINITY;
+}
+
+// final mask: first key above the k-th value, or selected by the second-key pass
+__global__ void __launch_bounds__(kBlock) k_round_merge(int64_t m, const double* __restrict__ t, const SelState* st1,
+                                                        const uint8_t* __restrict__ sel2, double* __restrict__ out) {
+    const unsigned long long kth = st1->prefix;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = (order_key(t[e]) > kth || sel2[e]) ? 1.0 : 0.0;
 }
 
 __global__ void __launch_bounds__(kBlock) k_mask_to_double(int64_t m, const uint8_t* __restrict__ sel, double* __restrict__ out) {

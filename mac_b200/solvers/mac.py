@@ -127,7 +127,7 @@ class MAC:
         if rounding == "madow":
             rounded = round_madow(w, k, value_fn=self.evaluate_objective, max_iters=random_rounding_max_iters)
         else:
-            rounded = round_nearest(w, k, weights=self.weights, break_ties_decimal_tol=10)  # mac.py:207
+            rounded = self._h.round_nearest(w, k, decimals=10)  # mac.py:207, weights = kappa already on the device
         rounding_time = timer() - start
         if fallback:
             # mac.py:211-218 intends "keep x_init if rounding made things worse" (it raises NameError

@@ -3,8 +3,8 @@
 `round_nearest(w, k)` without tie-break arguments is the LP oracle of the Frank-Wolfe loop
 (constraints.py:22) and runs on the device (`macb_topk_dense`: radix select, ties at the k-th
 value to the lowest index -- numpy's introselect leaves that order unspecified).
-The tie-broken variant (rounding.py:30-42) and Madow / random rounding run once per solve on the
-host as array code: they are "next" row 1 of SURVEY section 8f, not the hot loop.
+The tie-broken variant (rounding.py:30-42) is a two-key radix select on the device
+(`macb_round_nearest`); Madow / random rounding run once per solve on the host as array code.
 """
 from __future__ import annotations
 
@@ -22,16 +22,12 @@ def round_nearest(w, k, weights=None, break_ties_decimal_tol=None, device=-1):
         if k >= len(w):
             return np.ones(len(w))
         return _lib.topk_dense(w, k, device=device)
-    # rounding.py:33-42: lexicographic (w rounded to `tol` decimals, weight) top-k.
-    truncated_w = w.round(decimals=break_ties_decimal_tol)
-    zipped = np.empty(len(w), dtype=[("w", "float"), ("weight", "float")])
-    zipped["w"] = truncated_w
-    zipped["weight"] = np.asarray(weights, dtype=np.float64)
-    idx = np.argpartition(zipped, -k, order=["w", "weight"])[-k:]
-    rounded = np.zeros(len(w))
-    if k > 0:
-        rounded[idx] = 1.0
-    return rounded
+    # rounding.py:33-42: lexicographic (w rounded to `tol` decimals, weight) top-k, two-key radix select on the device
+    if k <= 0:
+        return np.zeros(len(w))
+    if k >= len(w):
+        return np.ones(len(w))
+    return _lib.round_nearest_dense(w, weights, k, int(break_ties_decimal_tol), device=device)
 
 
 def round_random(w, k):
