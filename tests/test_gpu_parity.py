@@ -481,3 +481,45 @@ def test_headline_size_properties():
     c = h.counters()
     assert c["kernel_launches"] > 0 and c["spmv_launches"] > 0
     mac.close()
+
+
+# ------------------------------------------------------------------------------------------- farm (multi-GPU)
+def _farm_rank(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from mac_b200 import farm
+        fixed, cand, n = synth.chain_plus_random(1500, 9000, seed=4, weighted=True)
+        budgets = [900, 1800, 2700, 3600]
+        res = farm.sweep_budgets(fixed, cand, n, budgets, lambda k: synth.first_k_init(9000, k), max_iters=5)
+        q.put((rank, [(k, int(r.sum()), float(u), float(lam)) for (k, r, w, u, lam) in res]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_farm_sweep_two_gpus_nccl():
+    """One budget sweep farmed over two GPUs (NCCL gather of the per-budget results) equals the single-GPU sweep."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_farm_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1] == out[1][1]
+    from mac_b200 import farm
+    fixed, cand, n = synth.chain_plus_random(1500, 9000, seed=4, weighted=True)
+    single = farm.sweep_budgets(fixed, cand, n, [900, 1800, 2700, 3600], lambda k: synth.first_k_init(9000, k), max_iters=5)
+    for (k, nsel, u, lam), (k1, r1, w1, u1, lam1) in zip(out[0][1], single):
+        assert k == k1 and nsel == k and abs(u - u1) <= 1e-9 * abs(u1) and abs(lam - lam1) <= 1e-9 * lam1
