@@ -88,6 +88,7 @@ struct macb_ctx {
     int persist_v = 3;             // 3: slot-parallel kernel (k_lanczos_slots); 1: row-parallel (k_lanczos_persist)
     int *d_chunk_ptr = nullptr, *d_chunk_row = nullptr;
     size_t slots_smem = 0;
+    int slots_cache_cols = 0, slots_prod_cap = 0;
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
     int* h_stop = nullptr;         // host-mapped
@@ -380,7 +381,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
         CK(cudaGetLastError());
     } else if (c->persist_v == 3) {
-        LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row};
+        LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
         void* params[] = {&a, &ch};
         CK(cudaLaunchCooperativeKernel((void*)k_lanczos_slots, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
     } else {
@@ -450,6 +451,14 @@ void setup_persist(macb_ctx* c) {
             CK(cudaMemcpyAsync(c->d_chunk_row, chunk_row.data(), sizeof(int) * chunk_row.size(), cudaMemcpyHostToDevice, c->stream));
             CK(cudaStreamSynchronize(c->stream));
             c->slots_smem = (size_t)max_slots * sizeof(double);
+            c->slots_prod_cap = (int)max_slots;
+            // one chunk per CTA and room for 4 more bytes per slot => keep the column indices in shared memory
+            bool single = true;
+            for (int b = 0; b < c->p_ncta; ++b) single = single && (chunk_ptr[b + 1] - chunk_ptr[b] <= 1);
+            if (single && (size_t)max_slots * 12 <= (size_t)224 * 1024 && !getenv("MACB_NO_COLCACHE")) {
+                c->slots_cache_cols = 1;
+                c->slots_smem = (size_t)max_slots * 12;
+            }
             CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
         }
     }

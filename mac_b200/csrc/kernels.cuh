@@ -616,6 +616,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
 struct LzChunkArgs {
     const int* chunk_ptr;   // [ncta + 1] chunks of CTA b are chunk_ptr[b] .. chunk_ptr[b+1]
     const int* chunk_row;   // [nchunks + 1] first row of every chunk (rows of chunk q: chunk_row[q] .. chunk_row[q+1])
+    int cache_cols;         // every CTA has one chunk and 12 bytes/slot fit in shared memory: column indices (with an
+                            // "inactive" bit for zero weights) stay in shared memory for the whole launch, so a gather
+                            // address never waits for a global load
+    int prod_cap;           // slots reserved for the product buffer (the column cache follows it)
 };
 
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, LzChunkArgs ch) {
@@ -628,6 +632,13 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
     const double* __restrict__ val = a.val;
     const int* __restrict__ rp = a.rp;
     const int q0 = ch.chunk_ptr[blockIdx.x], q1 = ch.chunk_ptr[blockIdx.x + 1];
+    int* __restrict__ scol = reinterpret_cast<int*>(prod + ch.prod_cap);
+    if (ch.cache_cols && q1 > q0) {
+        const int sa = rp[ch.chunk_row[q0]], sb = rp[ch.chunk_row[q0 + 1]];
+        for (int i = sa + (int)threadIdx.x; i < sb; i += kPBlock)
+            scol[i - sa] = ld_nc(col + i) | ((ld_nc(val + i) == 0.0) ? (int)0x80000000 : 0);
+        __syncthreads();
+    }
 
     int phase = a.st->phase;
     int cur = a.st->cur;
@@ -646,6 +657,53 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
 #ifdef MACB_PTIMING
         long long t_start = clock64();
 #endif
+        if (ch.cache_cols) {
+            // single chunk, column indices resident in shared memory
+            const int ra = ch.chunk_row[q0], rb = ch.chunk_row[q0 + 1];
+            const int row = ra + (int)threadIdx.x;
+            const bool has_row = (q1 > q0) && row < rb;
+            double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;
+            if (has_row) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
+            const int sa = (q1 > q0) ? rp[ra] : 0, sb = (q1 > q0) ? rp[rb] : 0;
+            const int ns = sb - sa;
+            for (int j0 = (int)threadIdx.x; j0 < ns; j0 += 4 * kPBlock) {
+                const int j1 = j0 + kPBlock, j2 = j0 + 2 * kPBlock, j3 = j0 + 3 * kPBlock;
+                const bool v1 = j1 < ns, v2 = j2 < ns, v3 = j3 < ns;
+                const int c0 = scol[j0], c1 = v1 ? scol[j1] : (int)0x80000000, c2 = v2 ? scol[j2] : (int)0x80000000,
+                          c3 = v3 ? scol[j3] : (int)0x80000000;
+                double z0, u0, g0, z1, u1, g1, z2, u2, g2, z3, u3, g3;
+                ld_sector_if(S + 4 * (size_t)(c0 & 0x7fffffff), c0 >= 0, z0, u0, g0);
+                ld_sector_if(S + 4 * (size_t)(c1 & 0x7fffffff), c1 >= 0, z1, u1, g1);
+                ld_sector_if(S + 4 * (size_t)(c2 & 0x7fffffff), c2 >= 0, z2, u2, g2);
+                ld_sector_if(S + 4 * (size_t)(c3 & 0x7fffffff), c3 >= 0, z3, u3, g3);
+                const double w0 = (c0 >= 0) ? ld_nc(val + sa + j0) : 0.0, w1 = (c1 >= 0) ? ld_nc(val + sa + j1) : 0.0,
+                             w2 = (c2 >= 0) ? ld_nc(val + sa + j2) : 0.0, w3 = (c3 >= 0) ? ld_nc(val + sa + j3) : 0.0;
+                prod[j0] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+                if (v1) prod[j1] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+                if (v2) prod[j2] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+                if (v3) prod[j3] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
+            }
+            __syncthreads();
+            if (has_row) {
+                const int s0 = rp[row] - sa, s1 = rp[row + 1] - sa;
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = s0;
+                for (; i + 1 < s1; i += 2) {
+                    acc0 += prod[i];
+                    acc1 += prod[i + 1];
+                }
+                if (i < s1) acc0 += prod[i];
+                const double t = fma(k1, oz, fma(k2, ou, k3 * oq));
+                const double un = t + k4;
+                const double zn = fma(od, t, -(acc0 + acc1));
+                st_sector(D + 4 * (size_t)row, zn, un, ou, od);
+                bj[row] = un;
+                p1 = fma(un, zn, p1);
+                p2 += zn;
+                p3 = fma(un, un, p3);
+                p4 += un;
+            }
+        } else
         for (int q = q0; q < q1; ++q) {
             const int ra = ch.chunk_row[q], rb = ch.chunk_row[q + 1];
             const int row = ra + (int)threadIdx.x;
