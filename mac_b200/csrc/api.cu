@@ -91,7 +91,11 @@ struct macb_ctx {
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
-    int* h_stop = nullptr;         // host-mapped
+    int* h_stop = nullptr;         // pinned: [0] = 1 (source of the stop push)
+    int* d_stop = nullptr;         // device flag the Lanczos kernel samples once per phase; the host raises it with a
+                                   // 4-byte async copy on side_stream (a PCIe read from inside the kernel would sit on
+                                   // CTA 0's critical path: its scoreboard slot is shared with the gathers)
+    cudaStream_t side_stream = nullptr;
     int ab_dirty = 0;              // h_ab entries [0, ab_dirty) may hold values of an earlier launch
     int p_ncta = 1;
     int* d_row_start = nullptr;
@@ -100,6 +104,12 @@ struct macb_ctx {
     LzPersistState* d_pst = nullptr;
     long long* d_ptiming = nullptr;
     std::vector<int32_t> h_rp;  // host copy of row_ptr (row partition)
+    std::vector<int32_t> h_col, h_eid;  // host copies of the pattern until the persistent engine has been set up
+    // jagged-diagonal staging of the slot-parallel kernel (k_lanczos_jds, persist_v == 5)
+    int *d_jrow = nullptr, *d_jlen = nullptr, *d_jcol = nullptr, *d_jeid = nullptr, *d_jd = nullptr;
+    double* d_jval = nullptr;
+    double* d_xrec = nullptr;      // all-to-all barrier inboxes of k_lanczos_jds
+    int jd_stride = 0;
 
     // reductions / selection
     double* d_partials = nullptr;
@@ -243,7 +253,7 @@ void free_all(macb_ctx* c) {
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
                      c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
-                     c->d_pst, c->d_ptiming};
+                     c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
@@ -252,6 +262,8 @@ void free_all(macb_ctx* c) {
     if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
     if (c->h_ab) cudaFreeHost(c->h_ab);
     if (c->h_stop) cudaFreeHost(c->h_stop);
+    if (c->d_stop) cudaFree(c->d_stop);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->it0) cudaEventDestroy(c->it0);
@@ -307,6 +319,10 @@ void launch_assemble(macb_ctx* c) {
     const int grid = c->grid_rows();
     DISPATCH_W(c->W, k_assemble<WW><<<grid, kBlock, 0, c->stream>>>(c->n, c->d_rp, c->d_eid, c->d_ew, c->d_val,
                                                                        c->d_diag, c->d_sc, c->ws()));
+    if (c->persist_v == 5) {
+        k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
+        c->c_launches++;
+    }
     CK(cudaGetLastError());
     c->c_launches++;
     CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -375,11 +391,15 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.st = c->d_pst;
     a.timing = c->d_ptiming;
     a.ab_host = async ? c->h_ab : nullptr;
-    a.stop = async ? c->h_stop : nullptr;
+    a.stop = async ? c->d_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
     if (c->persist_v == 4) {
         k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
         CK(cudaGetLastError());
+    } else if (c->persist_v == 5) {
+        LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec};
+        void* params[] = {&a, &J};
+        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_jds, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
     } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
         void* params[] = {&a, &ch};
@@ -460,9 +480,79 @@ void setup_persist(macb_ctx* c) {
                 c->slots_smem = (size_t)max_slots * 12;
             }
             CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+            // jagged-diagonal staging (k_lanczos_jds): one chunk per CTA, products + column cache + diagonal starts fit
+            const int64_t cap4 = (max_slots + 3) / 4 * 4;
+            const int64_t stride = (maxrow + 1 + 3) / 4 * 4;
+            if (single && c->slots_cache_cols && (size_t)cap4 * 12 + (size_t)stride * 4 <= (size_t)224 * 1024 && !getenv("MACB_NO_JDS") &&
+                !c->h_col.empty()) {
+                const int ncta = c->p_ncta;
+                std::vector<int> jrow((size_t)n), jlen((size_t)n), jcol((size_t)c->nnz), jeid((size_t)c->nnz),
+                    jd((size_t)ncta * stride, 0);
+                std::vector<int> order, cnt, inv((size_t)n);   // inv[caller id] = engine id
+                for (int b = 0; b < ncta; ++b) {
+                    const int ra = rs[b], R = rs[b + 1] - ra;
+                    order.resize(R);
+                    for (int t = 0; t < R; ++t) order[t] = ra + t;
+                    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+                        return c->h_rp[x + 1] - c->h_rp[x] > c->h_rp[y + 1] - c->h_rp[y];
+                    });
+                    for (int t = 0; t < R; ++t) {
+                        jrow[ra + t] = order[t];
+                        inv[order[t]] = ra + t;
+                    }
+                }
+                for (int b = 0; b < ncta; ++b) {
+                    const int ra = rs[b], rb = rs[b + 1], R = rb - ra;
+                    const int sa = c->h_rp[ra];
+                    cnt.assign((size_t)stride, 0);   // cnt[d] = rows with more than d slots
+                    for (int t = 0; t < R; ++t) {
+                        const int row = jrow[ra + t], len = c->h_rp[row + 1] - c->h_rp[row];
+                        jlen[ra + t] = len;
+                        for (int d = 0; d < len; ++d) cnt[d]++;
+                    }
+                    int* jdb = jd.data() + (size_t)b * stride;
+                    int acc = 0;
+                    for (int d = 0; d < stride; ++d) {
+                        jdb[d] = acc;
+                        acc += cnt[d];
+                    }
+                    for (int t = 0; t < R; ++t) {
+                        const int row = jrow[ra + t], s0 = c->h_rp[row], len = c->h_rp[row + 1] - s0;
+                        for (int d = 0; d < len; ++d) {
+                            jcol[(size_t)sa + jdb[d] + t] = inv[c->h_col[(size_t)s0 + d]];
+                            jeid[(size_t)sa + jdb[d] + t] = c->h_eid[(size_t)s0 + d];
+                        }
+                    }
+                }
+                c->d_jrow = dalloc<int>(n);
+                c->d_jlen = dalloc<int>(n);
+                c->d_jcol = dalloc<int>(c->nnz);
+                c->d_jeid = dalloc<int>(c->nnz);
+                c->d_jval = dalloc<double>(c->nnz);
+                c->d_jd = dalloc<int>(jd.size());
+                c->d_xrec = dalloc<double>((size_t)8 * ncta * ncta);
+                CK(cudaMemcpyAsync(c->d_jrow, jrow.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->d_jlen, jlen.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->d_jcol, jcol.data(), sizeof(int) * c->nnz, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->d_jeid, jeid.data(), sizeof(int) * c->nnz, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->d_jd, jd.data(), sizeof(int) * jd.size(), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                c->jd_stride = (int)stride;
+                c->slots_prod_cap = (int)cap4;
+                c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
+                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                c->persist_v = 5;
+                if (c->have_x) {   // L(x) was assembled before the engine existed: fill the jagged copy of the weights once
+                    k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
+                    CK(cudaGetLastError());
+                    c->c_launches++;
+                }
+            }
         }
     }
-    if (c->persist_v != 3 && c->persist_v != 4) {
+    std::vector<int32_t>().swap(c->h_col);
+    std::vector<int32_t>().swap(c->h_eid);
+    if (c->persist_v != 3 && c->persist_v != 4 && c->persist_v != 5) {
         // CTAs: one per SM at most (cooperative launch => all co-resident); small graphs use fewer so that the
         // grid barrier stays cheap.
         int64_t want = ((int64_t)c->n * c->W + kPBlock - 1) / kPBlock;
@@ -492,11 +582,15 @@ void setup_persist(macb_ctx* c) {
     c->d_pst = dalloc<LzPersistState>(1);
     CK(cudaMemsetAsync(c->d_pst, 0, sizeof(LzPersistState), c->stream));
     CK(cudaHostAlloc(&c->h_ab, sizeof(double) * 2 * (c->basis_cap + 2), cudaHostAllocMapped));
-    CK(cudaHostAlloc(&c->h_stop, sizeof(int) * 16, cudaHostAllocMapped));
-    *c->h_stop = 0;
+    CK(cudaHostAlloc(&c->h_stop, sizeof(int) * 16, cudaHostAllocDefault));
+    *c->h_stop = 1;
+    c->d_stop = dalloc<int>(16);
+    CK(cudaMemsetAsync(c->d_stop, 0, sizeof(int) * 16, c->stream));
+    CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     for (int64_t j = 0; j < 2 * (c->basis_cap + 2); ++j) c->h_ab[j] = std::numeric_limits<double>::quiet_NaN();
 #ifdef MACB_PTIMING
-    c->d_ptiming = dalloc<long long>((size_t)64 * c->p_ncta * 4);
+    c->d_ptiming = dalloc<long long>((size_t)64 * c->p_ncta * 9);
+    CK(cudaMemsetAsync(c->d_ptiming, 0, sizeof(long long) * 64 * c->p_ncta * 9, c->stream));
 #endif
 }
 
@@ -553,7 +647,8 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
     std::vector<double> coef(k);
     for (int t = 0; t < k; ++t) coef[t] = s[t] / c->h_beta[t];
     CK(cudaMemcpyAsync(c->d_coef, coef.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
-    k_ritz<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws());
+    k_ritz<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(),
+                                                        c->persist_v == 5 ? c->d_jrow : nullptr);
     k_center_normalize<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_sc);
     launch_spmv<2>(c, c->d_v, c->d_y);
     k_resid_l1<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_y, c->d_sc, c->ws());
@@ -601,7 +696,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 ab[2 * j + 1] = nan;
             }
             c->ab_dirty = phases_done;
-            *(volatile int*)c->h_stop = 0;
+            CK(cudaMemsetAsync(c->d_stop, 0, sizeof(int), c->stream));
             launch_persist(c, nph, true);
         }
         bool stopped = false;
@@ -647,9 +742,10 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             t_rr += us() - tw1;
             ++n_checks;
             if (est * sqrtn < tol * lnorm || exhausted) {
-                *(volatile int*)c->h_stop = 1;
+                CK(cudaMemcpyAsync(c->d_stop, c->h_stop, sizeof(int), cudaMemcpyHostToDevice, c->side_stream));
                 const double ts0 = us();
                 CK(cudaStreamSynchronize(c->stream));
+                CK(cudaStreamSynchronize(c->side_stream));   // the push has landed before the flag is cleared again
                 if (trace)
                     fprintf(stderr, "[macb] k=%d checks=%d wait=%.0fus rr=%.0fus stop->sync=%.0fus t=%.0fus\n", k, n_checks, t_wait, t_rr,
                             us() - ts0, us());
@@ -720,7 +816,8 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
         const double* src = use_warm ? c->d_v : c->d_x0;
         if (c->persist) {
             k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs,
-                                                                         2 * c->p_ncta);
+                                                                         2 * c->p_ncta, c->persist_v == 5 ? c->d_jrow : nullptr, c->d_xrec,
+                                                                         c->d_xrec ? (int64_t)8 * c->p_ncta * c->p_ncta : 0);
         } else {
             CK(cudaMemcpyAsync(c->d_basis, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
             k_set_lanczos_start<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_beta, c->d_usum, use_warm ? 1.0 : c->x0_norm);
@@ -982,6 +1079,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         c->nnz = (int64_t)col.size();
         c->W = pick_width((double)c->nnz / std::max(1, n));
         c->h_rp = rp;
+        c->h_col = col;
+        c->h_eid = eid;
         if (const char* env = getenv("MACB_LANCZOS")) c->persist = (std::string(env) != "graph");
         if (const char* env = getenv("MACB_PERSIST_STREAM")) c->persist_stream = atoi(env) != 0;
         if (const char* env = getenv("MACB_ASYNC")) c->async_rr = atoi(env) != 0;
@@ -1382,11 +1481,11 @@ int macb_iter_ms(macb_handle h, double* ms, int cap, int* count) {
 }
 
 #ifdef MACB_PTIMING
-extern "C" int macb_debug_ptiming(macb_handle h, long long* out /*[64][ncta][4]*/, int* ncta) {
+extern "C" int macb_debug_ptiming(macb_handle h, long long* out /*[64][ncta][4] + [64][ncta]*/, int* ncta) {
     return guarded(h, [&]() {
         if (ncta) *ncta = h->p_ncta;
         if (out && h->d_ptiming)
-            CK(cudaMemcpy(out, h->d_ptiming, sizeof(long long) * 64 * h->p_ncta * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out, h->d_ptiming, sizeof(long long) * 64 * h->p_ncta * 9, cudaMemcpyDeviceToHost));
         return (int)MACB_OK;
     });
 }

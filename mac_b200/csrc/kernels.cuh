@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
         if (blockIdx.x == 0 && threadIdx.x == 0 && a.stop)
             asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_now) : "l"(a.stop));
 #ifdef MACB_PTIMING
-        long long t_start = clock64();
+        long long t_start = clock64(), t_p1 = 0;
 #endif
         if (ch.cache_cols) {
             // single chunk, column indices resident in shared memory
@@ -684,6 +684,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
                 if (v3) prod[j3] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
             }
             __syncthreads();
+#ifdef MACB_PTIMING
+            t_p1 = clock64();
+#endif
             if (has_row) {
                 const int s0 = rp[row] - sa, s1 = rp[row + 1] - sa;
                 double acc0 = 0.0, acc1 = 0.0;
@@ -821,6 +824,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
         if (threadIdx.x == 0 && a.timing && it < 64) {
             long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
             t[0] = t_start; t[1] = t_rows; t[2] = t_bar; t[3] = clock64();
+            a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
         }
 #endif
         k1 = nk1; k2 = nk2; k3 = nk3; k4 = nk4;
@@ -838,6 +842,309 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = beta_prev;
         a.st->usum_prev = usum_prev;
+    }
+}
+
+// ---- K3, slot-parallel form with jagged-diagonal staging (default when every CTA's range is one chunk) ----------
+// Same state, recurrence, records and outputs as k_lanczos_slots.  Three differences, all aimed at the cycles of a
+// step that are NOT gathers (clock64 stamps on B200 at the headline size: gathers 16.8 k cycles = the L1TEX
+// divergent-gather floor, row sums + block reduce 6.0 k, barrier + record fetch 4.3-5.3 k, coefficient chain 0.9 k):
+//  * the slots of a CTA are stored in jagged-diagonal order (rows sorted by decreasing length, diagonal d = the
+//    d-th slot of every row that has one): pass 1 is unchanged (thread j <-> slot j, coalesced), and in pass 2
+//    thread t sums prod[jd[d] + t] -- consecutive threads read consecutive words, so the row sums are free of the
+//    ~4-way bank conflicts a CSR-ordered product buffer gives, and warps are uniform in trip count;
+//  * everything that is constant over the launch (row id, length, slot range, diagonal starts, column indices)
+//    lives in registers / shared memory: no global load sits between the barrier and the first gather;
+//  * the first batch of gathers of step j+1 is issued straight after the barrier of step j, BEFORE the CTA fetches
+//    the 148 partial-sum records and runs the (long-latency, double-precision) coefficient chain: the gathers need
+//    only addresses, the coefficients are needed when the products are formed.
+struct LzJdsArgs {
+    const int* row_start;   // [ncta + 1] rows of CTA b (<= kPBlock of them), in the ENGINE's node numbering
+    const int* jlen;        // [n]   number of slots of engine row i
+    const int* jcol;        // [nnz] column (engine numbering) of every slot, jagged-diagonal order inside a CTA's slot range
+    const double* jval;     // [nnz] weight of every slot, same order (k_assemble_jds)
+    const int* jd;          // [ncta * jd_stride] first CTA-local slot of diagonal d
+    int jd_stride;
+    int prod_cap;           // slots reserved for the product buffer; the column cache and jd follow
+    double* xrec;           // [2][ncta][ncta][4] inboxes of the all-to-all barrier, NaN = empty (k_lz_persist_init)
+};
+// Engine numbering: inside every CTA's row range the rows are renumbered by decreasing length (perm[new] = old), so
+// that thread t owns engine row ra + t and its sector / basis accesses stay coalesced.  k_lz_persist_init permutes
+// the start vector in, k_ritz permutes the Ritz vector out; nothing outside the Lanczos engine sees the numbering.
+
+__global__ void __launch_bounds__(kBlock) k_assemble_jds(int64_t nnz, const int* __restrict__ jeid,
+                                                         const double* __restrict__ ew, double* __restrict__ jval) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nnz; s += (int64_t)gridDim.x * blockDim.x)
+        jval[s] = ew[ld_stream(jeid + s)];
+}
+
+// Sum of four values over the 32 lanes of a warp with 6 double shuffles instead of 20: two halving steps in which
+// every lane sends away half of the values it still holds, then three plain butterfly steps on the one value left.
+// Every lane l ends with the warp total of value (l >> 3) & 3 ... precisely: bit 4 of the lane selects {0,1} vs {2,3},
+// bit 3 selects the even or odd member.  The shuffle network (SHFL) shares the MIO path with the gathers, so fewer
+// shuffles is fewer stalled cycles at the end of every step.
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
+    const bool hi = lane & 16;
+    // lanes with bit 4 set keep (v2, v3) and give away (v0, v1); the others the reverse
+    double s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
+    double k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool mid = lane & 8;
+    double s = mid ? k0 : k1, k = mid ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, s, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;   // lane l holds the total of value 2 * (l >> 4) + ((l >> 3) & 1)
+}
+
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJdsArgs J) {
+    extern __shared__ double prod[];
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double tot[4];
+    __shared__ int stop_sm;
+    __shared__ double carry[2][2];   // [parity][1/beta, sum(u)] of the last completed phase (kept out of registers)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
+    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
+    int* __restrict__ sjd = scol + J.prod_cap;
+    const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
+    const int sa = a.rp[ra], ns = a.rp[rb] - sa;
+    const bool has_row = tid < rb - ra;
+    const int row = ra + tid;
+    const int len = has_row ? J.jlen[row] : 0;
+    const double* __restrict__ jval = J.jval + sa;
+    for (int i = tid; i < ns; i += kPBlock)
+        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
+    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
+
+    int phase = a.st->phase;
+    int cur = a.st->cur;
+    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
+    if (tid == 0) {
+        carry[phase & 1][0] = a.st->beta_prev;   // 1/beta of the last completed step (slot of the NEXT phase's parity)
+        carry[phase & 1][1] = a.st->usum_prev;
+    }
+    __syncthreads();
+    const unsigned int ncta = (unsigned int)a.ncta;
+    const int j1 = tid + kPBlock, j2 = tid + 2 * kPBlock;
+    // early gathers per thread: slots per thread mod 4 (2 when that is 0)
+    const int per_thread = (ns + kPBlock - 1) / kPBlock;
+    const int E = (per_thread & 3) ? (per_thread & 3) : 2;
+    const double* const S0 = a.sect[0];
+    const double* const S1 = a.sect[1];
+    const double inv_n = 1.0 / (double)a.n;
+    const int rows_warps = (rb - ra + 31) >> 5;   // warps that own rows
+
+    for (int it = 0;; ++it) {
+        const bool more = it < a.nphases;
+        const double* __restrict__ S = cur ? S1 : S0;
+#ifdef MACB_PTIMING
+        long long t_start = clock64(), t_p1 = 0, t_coef = 0;
+#endif
+        // ---- totals of the phase that has just passed its barrier (shared memory), read BEFORE this thread's gathers
+        // enter the SM's memory pipe; the coefficient chain itself (one rsqrt + multiplications) runs after the
+        // first gathers have been issued and overlaps with their latency
+        double P1 = 0.0, P2 = 0.0, P3 = 0.0, P4 = 0.0, bprev = 0.0, uprev = 0.0;
+        int stop_all = 0;
+        if (it > 0) {
+            P1 = tot[0]; P2 = tot[1]; P3 = tot[2]; P4 = tot[3];
+            stop_all = stop_sm;
+            bprev = carry[(phase - 1) & 1][0];
+            uprev = carry[(phase - 1) & 1][1];
+        }
+        // ---- first E gathers of phase `phase` (they need addresses only); E = (slots per thread) mod 4 so that the
+        // main loop below runs full batches of four
+        double z0 = 0.0, u0 = 0.0, g0 = 0.0, z1 = 0.0, u1 = 0.0, g1 = 0.0, z2 = 0.0, u2 = 0.0, g2 = 0.0;
+        int c0 = (int)0x80000000, c1 = (int)0x80000000, c2 = (int)0x80000000;
+        int stop_now = 0;
+        if (more && !stop_all) {
+            if (blockIdx.x == 0 && tid == 0 && a.stop) stop_now = __ldcg(a.stop);
+            if (tid < ns) c0 = scol[tid];
+            if (E > 1 && j1 < ns) c1 = scol[j1];
+            if (E > 2 && j2 < ns) c2 = scol[j2];
+            ld_sector_if(S + 4 * (size_t)(c0 & 0x7fffffff), c0 >= 0, z0, u0, g0);
+            if (E > 1) ld_sector_if(S + 4 * (size_t)(c1 & 0x7fffffff), c1 >= 0, z1, u1, g1);
+            if (E > 2) ld_sector_if(S + 4 * (size_t)(c2 & 0x7fffffff), c2 >= 0, z2, u2, g2);
+        }
+        if (it > 0) {
+            const int done = phase - 1;
+            const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (done > 0) ? bprev : 0.0, uprev, inv_n);
+            k1 = cf.k1; k2 = cf.k2; k3 = cf.k3; k4 = cf.k4;
+            if (tid == 0) {
+                carry[phase & 1][0] = cf.binv;
+                carry[phase & 1][1] = P4;
+                if (blockIdx.x == 0) {
+                    a.alpha[done] = cf.alpha;
+                    a.beta[done] = cf.beta;
+                    if (a.ab_host)
+                        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)done), "d"(cf.alpha), "d"(cf.beta) : "memory");
+                }
+            }
+            if (stop_all) break;
+        }
+#ifdef MACB_PTIMING
+        t_coef = clock64();
+#endif
+        if (!more) break;
+        // ---- products: the early gathers, then the rest of the CTA's slots four at a time; the row's own sector is
+        // requested with the last batch (it is needed in pass 2 only)
+        double* __restrict__ D = cur ? a.sect[0] : a.sect[1];
+        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
+        double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;
+        {
+            const double w0 = (c0 >= 0) ? ld_nc(jval + tid) : 0.0;
+            if (tid < ns) prod[tid] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+            if (E > 1) {
+                const double w1 = (c1 >= 0) ? ld_nc(jval + j1) : 0.0;
+                if (j1 < ns) prod[j1] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+            }
+            if (E > 2) {
+                const double w2 = (c2 >= 0) ? ld_nc(jval + j2) : 0.0;
+                if (j2 < ns) prod[j2] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+            }
+        }
+        bool own_pending = has_row;
+        for (int b0 = tid + E * kPBlock; b0 < ns; b0 += 4 * kPBlock) {
+            const int b1 = b0 + kPBlock, b2 = b0 + 2 * kPBlock, b3 = b0 + 3 * kPBlock;
+            const bool v1 = b1 < ns, v2 = b2 < ns, v3 = b3 < ns;
+            double z3, u3, g3;
+            c0 = scol[b0];
+            c1 = v1 ? scol[b1] : (int)0x80000000;
+            c2 = v2 ? scol[b2] : (int)0x80000000;
+            const int c3 = v3 ? scol[b3] : (int)0x80000000;
+            if (own_pending && b0 + 4 * kPBlock >= ns) {
+                ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
+                own_pending = false;
+            }
+            ld_sector_if(S + 4 * (size_t)(c0 & 0x7fffffff), c0 >= 0, z0, u0, g0);
+            ld_sector_if(S + 4 * (size_t)(c1 & 0x7fffffff), c1 >= 0, z1, u1, g1);
+            ld_sector_if(S + 4 * (size_t)(c2 & 0x7fffffff), c2 >= 0, z2, u2, g2);
+            ld_sector_if(S + 4 * (size_t)(c3 & 0x7fffffff), c3 >= 0, z3, u3, g3);
+            const double w0 = (c0 >= 0) ? ld_nc(jval + b0) : 0.0, w1 = (c1 >= 0) ? ld_nc(jval + b1) : 0.0,
+                         w2 = (c2 >= 0) ? ld_nc(jval + b2) : 0.0, w3 = (c3 >= 0) ? ld_nc(jval + b3) : 0.0;
+            prod[b0] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+            if (v1) prod[b1] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+            if (v2) prod[b2] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+            if (v3) prod[b3] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
+        }
+        if (own_pending) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);   // rows of a CTA whose loop this thread never entered
+        __syncthreads();
+#ifdef MACB_PTIMING
+        t_p1 = clock64();
+#endif
+        // ---- row sums along the jagged diagonals (conflict-free), new sector, basis entry, partial sums
+        if (warp < rows_warps) {
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+            if (has_row) {
+                const double* __restrict__ pt = prod + tid;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int d = 0;
+                for (; d + 4 <= len; d += 4) {
+                    const int4 o = *reinterpret_cast<const int4*>(sjd + d);
+                    a0 += pt[o.x];
+                    a1 += pt[o.y];
+                    a2 += pt[o.z];
+                    a3 += pt[o.w];
+                }
+                for (; d < len; ++d) a0 += pt[sjd[d]];
+                const double acc = (a0 + a1) + (a2 + a3);
+                const double t = fma(k1, oz, fma(k2, ou, k3 * oq));
+                const double un = t + k4;                  // u_phase[row]
+                const double zn = fma(od, t, -acc);        // (L u_phase)[row]; L 1 = 0 cancels k4
+                st_sector(D + 4 * (size_t)row, zn, un, ou, od);
+                bj[row] = un;
+                p1 = un * zn;
+                p2 = zn;
+                p3 = un * un;
+                p4 = un;
+            }
+            const double r = warp_sum4(p1, p2, p3, p4, lane);
+            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        long long t_rows = clock64();
+#endif
+        // ---- grid barrier = all-to-all exchange of the CTAs' partial sums.  Every CTA pushes its 32-byte record into
+        // a slot of EVERY CTA's private inbox (after a gpu-scope fence, so its sectors are visible first) and polls
+        // its own inbox until all slots are valid (the inbox is NaN-filled between uses; NaN partial sums are
+        // replaced by +inf at the source).  No atomic, no shared hot line (all readers polling one counter and then
+        // fetching the same 148 records cost 2-6 k cycles of L2 serialisation per step), and the data needed after
+        // the barrier IS the barrier.  CTA 0's stop decision rides on the sign of its (non-negative) sum of squares.
+#ifdef MACB_PTIMING
+        long long tb0 = 0, tb1 = 0, tb2 = 0, tb3 = 0;
+#endif
+        if (warp == 0) {
+            const double x0 = (lane < rows_warps) ? sm[lane] : 0.0, x1 = (lane < rows_warps) ? sm[kPWarps + lane] : 0.0,
+                         x2 = (lane < rows_warps) ? sm[2 * kPWarps + lane] : 0.0, x3 = (lane < rows_warps) ? sm[3 * kPWarps + lane] : 0.0;
+            const double r = warp_sum4(x0, x1, x2, x3, lane);
+            double q0 = __shfl_sync(0xffffffffu, r, 0), q1 = __shfl_sync(0xffffffffu, r, 8),
+                   q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
+            const double inf = __longlong_as_double(0x7ff0000000000000ll);
+            q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
+            if (blockIdx.x == 0 && __shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
+            double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
+#ifdef MACB_PTIMING
+            tb0 = clock64();
+#endif
+            __threadfence();
+#ifdef MACB_PTIMING
+            tb1 = clock64();
+#endif
+            for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
+            const double* const mine = box + (size_t)blockIdx.x * ncta * 4;
+            double y0, y1, y2, y3;
+            int stop_seen;
+            unsigned int spins = 0;
+            while (true) {
+                bool ok = true;
+                y0 = y1 = y2 = y3 = 0.0;
+                stop_seen = 0;
+                for (unsigned int b = lane; b < ncta; b += 32) {
+                    double r0, r1, r2, r3;
+                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
+                    ok = ok && (r0 == r0) && (r1 == r1) && (r2 == r2) && (r3 == r3);
+                    if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
+                    y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > (1u << 22)) break;   // ~seconds: never hang the device on a lost CTA; the sums are then NaN
+            }
+            // (no acquire fence: the next step's gathers are .cg loads issued after this warp-uniform exit and the
+            //  __syncthreads below; the writers fenced before pushing, so the sectors are in L2 by now)
+#ifdef MACB_PTIMING
+            tb2 = clock64();
+#endif
+            const double t = warp_sum4(y0, y1, y2, y3, lane);
+            if ((lane & 7) == 0) tot[lane >> 3] = t;
+            if (lane == 0) stop_sm = stop_seen;
+            const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+            for (unsigned int b = lane; b < ncta; b += 32) st_sector(const_cast<double*>(mine) + (size_t)b * 4, nanv, nanv, nanv, nanv);
+#ifdef MACB_PTIMING
+            tb3 = clock64();
+#endif
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        if (tid == 0 && a.timing && it < 64) {
+            long long* e = a.timing + (size_t)64 * a.ncta * 5 + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            e[0] = tb0; e[1] = tb1; e[2] = tb2; e[3] = tb3;
+            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = t_coef;
+            a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
+        }
+#endif
+        cur ^= 1;
+        ++phase;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.st->phase = phase;
+        a.st->cur = cur;
+        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
+        a.st->beta_prev = carry[phase & 1][0];
+        a.st->usum_prev = carry[phase & 1][1];
     }
 }
 
@@ -1016,9 +1323,15 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, c
 // sectors for phase 0: (0, src_i, 0, diag_i) with (k1,k2,k3,k4) = (0,1,0,0)  =>  u_0 = src
 __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double* __restrict__ src,
                                                             const double* __restrict__ diag, double* __restrict__ sect0,
-                                                            LzPersistState* st, LzPartRec* recs, int nrecs) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        st_sector(sect0 + 4 * (size_t)i, 0.0, src[i], 0.0, diag[i]);
+                                                            LzPersistState* st, LzPartRec* recs, int nrecs,
+                                                            const int* __restrict__ perm /* engine -> caller numbering, or null */,
+                                                            double* __restrict__ xrec, int64_t nxrec /* inboxes <- NaN */) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxrec; i += (int64_t)gridDim.x * blockDim.x)
+        xrec[i] = __longlong_as_double(0x7ff8000000000000ll);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int o = perm ? perm[i] : i;
+        st_sector(sect0 + 4 * (size_t)i, 0.0, src[o], 0.0, diag[o]);
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrecs; i += gridDim.x * blockDim.x) recs[i].tag = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->phase = 0;
@@ -1034,7 +1347,8 @@ __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double*
 // y_raw = sum_t coef[t] basis[t]   (coef[t] = s_t / beta[t] folds the normalisation of u_t)
 __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const double* __restrict__ basis,
                                                  const double* __restrict__ coef, double* __restrict__ out,
-                                                 LzScalars* sc, ReduceWS ws) {
+                                                 LzScalars* sc, ReduceWS ws,
+                                                 const int* __restrict__ perm /* engine -> caller numbering, or null */) {
     __shared__ double sm[2 * kWarpsPerBlock];
     __shared__ int flag;
     double r0 = 0.0, r1 = 0.0;
@@ -1047,7 +1361,7 @@ __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const dou
         }
         for (; t < k; ++t) acc[0] = fma(coef[t], basis[(size_t)t * ld + i], acc[0]);
         double yv = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        out[i] = yv;
+        out[perm ? perm[i] : i] = yv;
         r0 += yv;
         r1 = fma(yv, yv, r1);
     }

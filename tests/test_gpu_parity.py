@@ -167,11 +167,13 @@ def test_warm_start_reaches_the_same_pair():
     mac.close()
 
 
-@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"},
+@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"},
+                                 {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
                                  {"MACB_PERSIST_V": "1", "MACB_ASYNC": "0", "MACB_PERSIST_STREAM": "1"}])
 def test_lanczos_engines_agree(monkeypatch, env):
-    """The default engine (slot-parallel persistent kernel + asynchronous host Rayleigh-Ritz) against the
-    alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel persistent kernel, synchronous batches."""
+    """The default engine (slot-parallel persistent kernel with jagged-diagonal staging + asynchronous host
+    Rayleigh-Ritz) against the alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel persistent
+    kernel, synchronous batches, CSR-ordered slot kernel with and without the shared-memory column cache."""
     fixed, cand, n = synth.chain_plus_random(4000, 40000, seed=3, weighted=True)
     x = synth.first_k_init(40000, 8000)
     ref = MAC(fixed, cand, n)
