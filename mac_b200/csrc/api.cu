@@ -91,11 +91,8 @@ struct macb_ctx {
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
-    int* h_stop = nullptr;         // pinned: [0] = 1 (source of the stop push)
-    int* d_stop = nullptr;         // device flag the Lanczos kernel samples once per phase; the host raises it with a
-                                   // 4-byte async copy on side_stream (a PCIe read from inside the kernel would sit on
-                                   // CTA 0's critical path: its scoreboard slot is shared with the gathers)
-    cudaStream_t side_stream = nullptr;
+    int* h_stop = nullptr;         // host-mapped stop flag (the Lanczos kernels sample it once per phase)
+    int check_div = 8;             // Rayleigh-Ritz check interval = k / check_div (24 when the graph fills the GPU)
     int ab_dirty = 0;              // h_ab entries [0, ab_dirty) may hold values of an earlier launch
     int p_ncta = 1;
     int* d_row_start = nullptr;
@@ -262,8 +259,6 @@ void free_all(macb_ctx* c) {
     if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
     if (c->h_ab) cudaFreeHost(c->h_ab);
     if (c->h_stop) cudaFreeHost(c->h_stop);
-    if (c->d_stop) cudaFree(c->d_stop);
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->it0) cudaEventDestroy(c->it0);
@@ -391,7 +386,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.st = c->d_pst;
     a.timing = c->d_ptiming;
     a.ab_host = async ? c->h_ab : nullptr;
-    a.stop = async ? c->d_stop : nullptr;
+    a.stop = async ? c->h_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
     if (c->persist_v == 4) {
         k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
@@ -573,6 +568,8 @@ void setup_persist(macb_ctx* c) {
             rs[b] = row;
         }
     }
+    c->check_div = (c->p_ncta >= c->sm_count) ? 24 : 8;
+    if (const char* env = getenv("MACB_CHECK_DIV")) c->check_div = std::max(1, atoi(env));
     c->d_row_start = dalloc<int>(c->p_ncta + 1);
     CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -582,11 +579,8 @@ void setup_persist(macb_ctx* c) {
     c->d_pst = dalloc<LzPersistState>(1);
     CK(cudaMemsetAsync(c->d_pst, 0, sizeof(LzPersistState), c->stream));
     CK(cudaHostAlloc(&c->h_ab, sizeof(double) * 2 * (c->basis_cap + 2), cudaHostAllocMapped));
-    CK(cudaHostAlloc(&c->h_stop, sizeof(int) * 16, cudaHostAllocDefault));
-    *c->h_stop = 1;
-    c->d_stop = dalloc<int>(16);
-    CK(cudaMemsetAsync(c->d_stop, 0, sizeof(int) * 16, c->stream));
-    CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CK(cudaHostAlloc(&c->h_stop, sizeof(int) * 16, cudaHostAllocMapped));
+    *c->h_stop = 0;
     for (int64_t j = 0; j < 2 * (c->basis_cap + 2); ++j) c->h_ab[j] = std::numeric_limits<double>::quiet_NaN();
 #ifdef MACB_PTIMING
     c->d_ptiming = dalloc<long long>((size_t)64 * c->p_ncta * 9);
@@ -665,7 +659,12 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
 
 // Check points of the asynchronous Rayleigh-Ritz: a function of k alone, so that the step count at which a solve
 // stops -- and with it the result, to the last bit -- does not depend on host/device timing.
-inline int next_check(int k) { return k + std::max(16, 16 * (k / 128)); }
+// A check costs the host ~0.055 us * k (Sturm multisection + eigenvector of T_k) and runs beside the kernel, whose
+// steps take 3.7 us (single-SM kernel) to 14 us (headline size): an interval of k/24 keeps the host below ~36 % duty at
+// any k, so it never falls behind, and the expected overshoot is k/48 steps (2 %) instead of 6 % at k/8.  That holds
+// for graphs that fill the GPU; on pose graphs (steps of 3.7-5.5 us, T_k with lambda_2/lambda_max ~ 1e-5 and thousands
+// of steps) the host would be the bottleneck, so they keep k/8 (macb_ctx::check_div, a function of the graph only).
+inline int next_check(int k, int div) { return k + std::max(div == 24 ? 4 : 16, (k / div) & ~3); }
 
 // One Lanczos cycle on the persistent engine with the host Rayleigh-Ritz running concurrently with the kernel.
 // Returns: 1 converged (result in `out`, vector in d_v), 0 cycle exhausted without convergence (best Ritz vector
@@ -696,7 +695,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 ab[2 * j + 1] = nan;
             }
             c->ab_dirty = phases_done;
-            CK(cudaMemsetAsync(c->d_stop, 0, sizeof(int), c->stream));
+            *(volatile int*)c->h_stop = 0;
             launch_persist(c, nph, true);
         }
         bool stopped = false;
@@ -706,11 +705,14 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             const int need = std::min(k_next, k_limit);
             bool kernel_done = false;
             const double tw0 = us();
-            while (std::isnan(ab[2 * need + 1])) {
-                if (cudaStreamQuery(c->stream) != cudaErrorNotReady) {
+            // spin on the mapped memory; ask the driver whether the kernel has ended only now and then (the query
+            // takes the driver lock: with several handles sweeping budgets concurrently that lock is the bottleneck)
+            for (unsigned int spin = 1; std::isnan(ab[2 * need + 1]); ++spin) {
+                if ((spin & 1023u) == 0 && cudaStreamQuery(c->stream) != cudaErrorNotReady) {
                     kernel_done = true;
                     break;
                 }
+                __builtin_ia32_pause();
             }
             if (kernel_done && std::isnan(ab[2 * need + 1])) {
                 CK(cudaStreamSynchronize(c->stream));  // surfaces launch/runtime errors
@@ -742,10 +744,9 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             t_rr += us() - tw1;
             ++n_checks;
             if (est * sqrtn < tol * lnorm || exhausted) {
-                CK(cudaMemcpyAsync(c->d_stop, c->h_stop, sizeof(int), cudaMemcpyHostToDevice, c->side_stream));
+                *(volatile int*)c->h_stop = 1;
                 const double ts0 = us();
                 CK(cudaStreamSynchronize(c->stream));
-                CK(cudaStreamSynchronize(c->side_stream));   // the push has landed before the flag is cleared again
                 if (trace)
                     fprintf(stderr, "[macb] k=%d checks=%d wait=%.0fus rr=%.0fus stop->sync=%.0fus t=%.0fus\n", k, n_checks, t_wait, t_rr,
                             us() - ts0, us());
@@ -776,9 +777,9 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                     return invariant ? -1 : 0;
                 }
                 // estimate passed but the true residual did not: resume the kernel and look again a little later
-                k_next = next_check(need);
+                k_next = next_check(need, c->check_div);
             } else {
-                k_next = next_check(need);
+                k_next = next_check(need, c->check_div);
             }
         }
         (void)k_conv;

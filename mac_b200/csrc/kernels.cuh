@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
     __shared__ double sm[4 * kPWarps];
     __shared__ double tot[4];
     __shared__ int stop_sm;
+    __shared__ int stop_in;
     __shared__ double carry[2][2];   // [parity][1/beta, sum(u)] of the last completed phase (kept out of registers)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
     int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
@@ -959,7 +960,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
         int c0 = (int)0x80000000, c1 = (int)0x80000000, c2 = (int)0x80000000;
         int stop_now = 0;
         if (more && !stop_all) {
-            if (blockIdx.x == 0 && tid == 0 && a.stop) stop_now = __ldcg(a.stop);
+            // the stop flag lives in host-mapped memory (a PCIe round trip): fetch it with cp.async so that its latency
+            // is not tied to the scoreboard slots of this warp's gathers; it is consumed at the end of the step
+            if (blockIdx.x == 0 && tid == 0 && a.stop)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(&stop_in)), "l"(a.stop) : "memory");
             if (tid < ns) c0 = scol[tid];
             if (E > 1 && j1 < ns) c1 = scol[j1];
             if (E > 2 && j2 < ns) c2 = scol[j2];
@@ -1083,7 +1087,13 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
                    q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
             q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
-            if (blockIdx.x == 0 && __shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
+            if (blockIdx.x == 0 && a.stop) {
+                if (lane == 0) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    stop_now = *(volatile int*)&stop_in;
+                }
+                if (__shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
+            }
             double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
 #ifdef MACB_PTIMING
             tb0 = clock64();
