@@ -89,6 +89,7 @@ struct macb_ctx {
     int *d_chunk_ptr = nullptr, *d_chunk_row = nullptr;
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
+    bool jds_sorted = false;
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
     int* h_stop = nullptr;         // host-mapped stop flag (the Lanczos kernels sample it once per phase)
@@ -394,7 +395,8 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     } else if (c->persist_v == 5) {
         LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec};
         void* params[] = {&a, &J};
-        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_jds, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
+        CK(cudaLaunchCooperativeKernel(c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>, dim3(a.ncta),
+                                       dim3(kPBlock), params, c->slots_smem, c->stream));
     } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
         void* params[] = {&a, &ch};
@@ -519,6 +521,26 @@ void setup_persist(macb_ctx* c) {
                         }
                     }
                 }
+                // optional: store every CTA's slots in column order (positions of the products packed beside the column)
+                c->jds_sorted = !(getenv("MACB_JDS_SORT") && atoi(getenv("MACB_JDS_SORT")) == 0) && n <= (1 << 17) && cap4 <= (1 << 14);
+                if (c->jds_sorted) {
+                    std::vector<std::pair<int, int>> key;
+                    std::vector<int> tc, te;
+                    for (int b = 0; b < ncta; ++b) {
+                        const int sa = c->h_rp[rs[b]], ns = c->h_rp[rs[b + 1]] - sa;
+                        key.resize(ns);
+                        for (int q = 0; q < ns; ++q) key[q] = {jcol[(size_t)sa + q], q};
+                        std::sort(key.begin(), key.end());
+                        tc.resize(ns);
+                        te.resize(ns);
+                        for (int q = 0; q < ns; ++q) {
+                            tc[q] = key[q].first | (key[q].second << 17);
+                            te[q] = jeid[(size_t)sa + key[q].second];
+                        }
+                        std::copy(tc.begin(), tc.end(), jcol.begin() + sa);
+                        std::copy(te.begin(), te.end(), jeid.begin() + sa);
+                    }
+                }
                 c->d_jrow = dalloc<int>(n);
                 c->d_jlen = dalloc<int>(n);
                 c->d_jcol = dalloc<int>(c->nnz);
@@ -535,7 +557,8 @@ void setup_persist(macb_ctx* c) {
                 c->jd_stride = (int)stride;
                 c->slots_prod_cap = (int)cap4;
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
-                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 c->persist_v = 5;
                 if (c->have_x) {   // L(x) was assembled before the engine existed: fill the jagged copy of the weights once
                     k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);

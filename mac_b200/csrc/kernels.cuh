@@ -899,7 +899,13 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
     return k;   // lane l holds the total of value 2 * (l >> 4) + ((l >> 3) & 1)
 }
 
+// SORTED: the CTA's slots are stored in column order (lanes of a warp then share 128-byte lines of the sector array,
+// which is what the L1TEX stage charges for) and every slot carries the position of its product in the jagged
+// diagonal buffer: scol = column (17 bits) | position (14 bits) << 17 | inactive << 31.
+template <bool SORTED>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJdsArgs J) {
+    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
+#define MACB_DST(cc, jj) (SORTED ? (((cc) >> 17) & 0x3fff) : (jj))
     extern __shared__ double prod[];
     __shared__ double sm[4 * kPWarps];
     __shared__ double tot[4];
@@ -967,9 +973,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
             if (tid < ns) c0 = scol[tid];
             if (E > 1 && j1 < ns) c1 = scol[j1];
             if (E > 2 && j2 < ns) c2 = scol[j2];
-            ld_sector_if(S + 4 * (size_t)(c0 & 0x7fffffff), c0 >= 0, z0, u0, g0);
-            if (E > 1) ld_sector_if(S + 4 * (size_t)(c1 & 0x7fffffff), c1 >= 0, z1, u1, g1);
-            if (E > 2) ld_sector_if(S + 4 * (size_t)(c2 & 0x7fffffff), c2 >= 0, z2, u2, g2);
+            ld_sector_if(S + 4 * (size_t)(c0 & CM), c0 >= 0, z0, u0, g0);
+            if (E > 1) ld_sector_if(S + 4 * (size_t)(c1 & CM), c1 >= 0, z1, u1, g1);
+            if (E > 2) ld_sector_if(S + 4 * (size_t)(c2 & CM), c2 >= 0, z2, u2, g2);
         }
         if (it > 0) {
             const int done = phase - 1;
@@ -998,14 +1004,14 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
         double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;
         {
             const double w0 = (c0 >= 0) ? ld_nc(jval + tid) : 0.0;
-            if (tid < ns) prod[tid] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+            if (tid < ns) prod[MACB_DST(c0, tid)] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
             if (E > 1) {
                 const double w1 = (c1 >= 0) ? ld_nc(jval + j1) : 0.0;
-                if (j1 < ns) prod[j1] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+                if (j1 < ns) prod[MACB_DST(c1, j1)] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
             }
             if (E > 2) {
                 const double w2 = (c2 >= 0) ? ld_nc(jval + j2) : 0.0;
-                if (j2 < ns) prod[j2] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+                if (j2 < ns) prod[MACB_DST(c2, j2)] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
             }
         }
         bool own_pending = has_row;
@@ -1021,16 +1027,16 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
                 ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
                 own_pending = false;
             }
-            ld_sector_if(S + 4 * (size_t)(c0 & 0x7fffffff), c0 >= 0, z0, u0, g0);
-            ld_sector_if(S + 4 * (size_t)(c1 & 0x7fffffff), c1 >= 0, z1, u1, g1);
-            ld_sector_if(S + 4 * (size_t)(c2 & 0x7fffffff), c2 >= 0, z2, u2, g2);
-            ld_sector_if(S + 4 * (size_t)(c3 & 0x7fffffff), c3 >= 0, z3, u3, g3);
+            ld_sector_if(S + 4 * (size_t)(c0 & CM), c0 >= 0, z0, u0, g0);
+            ld_sector_if(S + 4 * (size_t)(c1 & CM), c1 >= 0, z1, u1, g1);
+            ld_sector_if(S + 4 * (size_t)(c2 & CM), c2 >= 0, z2, u2, g2);
+            ld_sector_if(S + 4 * (size_t)(c3 & CM), c3 >= 0, z3, u3, g3);
             const double w0 = (c0 >= 0) ? ld_nc(jval + b0) : 0.0, w1 = (c1 >= 0) ? ld_nc(jval + b1) : 0.0,
                          w2 = (c2 >= 0) ? ld_nc(jval + b2) : 0.0, w3 = (c3 >= 0) ? ld_nc(jval + b3) : 0.0;
-            prod[b0] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
-            if (v1) prod[b1] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
-            if (v2) prod[b2] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
-            if (v3) prod[b3] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
+            prod[MACB_DST(c0, b0)] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
+            if (v1) prod[MACB_DST(c1, b1)] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
+            if (v2) prod[MACB_DST(c2, b2)] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
+            if (v3) prod[MACB_DST(c3, b3)] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
         }
         if (own_pending) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);   // rows of a CTA whose loop this thread never entered
         __syncthreads();
@@ -1157,6 +1163,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
         a.st->usum_prev = carry[phase & 1][1];
     }
 }
+#undef MACB_DST
 
 // ---- K3, single-CTA form for small graphs (pose graphs with n up to 3072 nodes, 12288 slots) -------------
 // When 24 n + 16 nnz bytes fit in one SM's shared memory the whole problem lives on that SM: (z, u, u') per

@@ -167,7 +167,7 @@ def test_warm_start_reaches_the_same_pair():
     mac.close()
 
 
-@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"},
+@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"}, {"MACB_JDS_SORT": "0"},
                                  {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
                                  {"MACB_PERSIST_V": "1", "MACB_ASYNC": "0", "MACB_PERSIST_STREAM": "1"}])
 def test_lanczos_engines_agree(monkeypatch, env):
