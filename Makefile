@@ -19,5 +19,8 @@ clean:
 .PHONY: all clean ptxas-info
 
 # debug variant with per-phase clock64 stamps inside the persistent Lanczos kernel (tools/ptiming.py)
+debugvec: $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -DMACB_DEBUG_VEC -shared -o mac_b200/libmacb200_debug.so $(SRC)
+
 timing: $(SRC) $(HDR)
 	$(NVCC) $(NVFLAGS) -DMACB_PTIMING -shared -o mac_b200/libmacb200_timing.so $(SRC)

@@ -90,6 +90,7 @@ struct macb_ctx {
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool jds_sorted = false;
+    bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
     int* h_stop = nullptr;         // host-mapped stop flag (the Lanczos kernels sample it once per phase)
@@ -393,10 +394,12 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
         CK(cudaGetLastError());
     } else if (c->persist_v == 5) {
-        LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec};
+        LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
+                    c->d_diag, c->d_jrow};
         void* params[] = {&a, &J};
-        CK(cudaLaunchCooperativeKernel(c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>, dim3(a.ncta),
-                                       dim3(kPBlock), params, c->slots_smem, c->stream));
+        void* fn = c->jds_vec ? (c->jds_sorted ? (void*)k_lanczos_vec<true> : (void*)k_lanczos_vec<false>)
+                              : (c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>);
+        CK(cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
     } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
         void* params[] = {&a, &ch};
@@ -559,6 +562,9 @@ void setup_persist(macb_ctx* c) {
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                c->jds_vec = !getenv("MACB_NO_VEC");
                 c->persist_v = 5;
                 if (c->have_x) {   // L(x) was assembled before the engine existed: fill the jagged copy of the weights once
                     k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
@@ -620,7 +626,7 @@ void ensure_basis(macb_ctx* c, int max_steps) {
     cap = (cap / kGraphSteps) * kGraphSteps;
     (void)max_steps;
     c->basis_cap = cap;
-    c->d_basis = dalloc<double>((size_t)(cap + 1) * c->ld);
+    c->d_basis = dalloc<double>((size_t)(cap + 2) * c->ld);   // k_lanczos_vec writes u_{j+1} at the end of phase j
     c->d_alpha = dalloc<double>(cap + 1);
     c->d_beta = dalloc<double>(cap + 2);
     c->d_ysum = dalloc<double>(cap + 1);
@@ -746,6 +752,11 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             for (int j = k_seen; j <= need; ++j) {
                 c->h_alpha[j] = ab[2 * j];
                 c->h_beta[j] = ab[2 * j + 1];
+                if (!std::isfinite(c->h_alpha[j]) || !std::isfinite(c->h_beta[j])) {
+                    *(volatile int*)c->h_stop = 1;
+                    cudaStreamSynchronize(c->stream);
+                    throw ArgFail{"macb_fiedler: the Lanczos recurrence produced a non-finite coefficient", MACB_ERR_STATE};
+                }
             }
             k_seen = std::max(k_seen, need + 1);
             int k = need;
@@ -838,7 +849,10 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     for (int restart = 0; restart < 64; ++restart) {
         // ---- (re)start
         const double* src = use_warm ? c->d_v : c->d_x0;
-        if (c->persist) {
+        if (c->persist && c->persist_v == 5 && c->jds_vec) {
+            k_lz_vec_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_jrow, c->d_sect[0], c->d_sect[1], c->d_xrec,
+                                                                     (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
+        } else if (c->persist) {
             k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs,
                                                                          2 * c->p_ncta, c->persist_v == 5 ? c->d_jrow : nullptr, c->d_xrec,
                                                                          c->d_xrec ? (int64_t)8 * c->p_ncta * c->p_ncta : 0);

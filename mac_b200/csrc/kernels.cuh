@@ -867,6 +867,8 @@ struct LzJdsArgs {
     int jd_stride;
     int prod_cap;           // slots reserved for the product buffer; the column cache and jd follow
     double* xrec;           // [2][ncta][ncta][4] inboxes of the all-to-all barrier, NaN = empty (k_lz_persist_init)
+    const double* diag;     // [n] weighted degrees, caller numbering (k_lanczos_vec keeps its row's in a register)
+    const int* perm;        // [n] engine -> caller numbering
 };
 // Engine numbering: inside every CTA's row range the rows are renumbered by decreasing length (perm[new] = old), so
 // that thread t owns engine row ra + t and its sector / basis accesses stay coalesced.  k_lz_persist_init permutes
@@ -1164,6 +1166,300 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
     }
 }
 #undef MACB_DST
+
+// ---- K3, materialised-vector form of the jagged-diagonal kernel (default when it applies) ------------------------
+// What the L1TEX stage charges for a gather is the number of distinct 128-byte lines a warp instruction touches.  A
+// 32-byte sector per node puts 4 nodes in a line; a plain vector of doubles puts 16.  With the CTA's slots stored in
+// column order, 32 consecutive lanes then touch ~12 lines instead of ~24 (headline graph: 5.7 k instead of 11.2 k
+// wavefronts per CTA and step).  So this kernel keeps u_j itself in global memory (two buffers of n doubles) and pays
+// for it with a short local pass after the barrier:
+//   pass 1   prod[dest_s] = w_s * U[col_s]                      (8-byte gathers, 8 in flight per thread)
+//   pass 2   z_i = d_i u_i - sum_s prod;  partial sums (u.z, sum z, u.u, sum u)         (rows of this CTA)
+//   barrier  all-to-all exchange of the partial sums (as k_lanczos_jds)  ->  alpha_j, beta_j, k1..k4
+//   pass B   u_{j+1}[i] = k1 z_i + k2 u_j[i] + k3 u_{j-1}[i] + k4  for the CTA's own rows (z, u_j, u_{j-1} are in
+//            registers); written to the other buffer and to the basis; the buffer just read is poisoned with NaN
+// There is no second barrier: a consumer that gathers NaN from the new buffer (its producer has not written yet)
+// gathers again.  The poison store of phase j is ordered before the producer's record push of phase j+1 by the
+// release fence of the exchange, so no consumer can see a value older than the poison.
+__device__ __forceinline__ double ld_f64_if(const double* p, bool pred) {
+    double v;
+    // relaxed.gpu, not a weak .cg load: the retry loop below re-reads the same address until the producer's store
+    // arrives, and ptxas is free to hoist a WEAK load out of such a loop (it did)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.relaxed.gpu.global.f64 %0, [%1];\n\t}"
+                 : "=d"(v) : "l"(p), "r"((int)pred) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_lz_vec_init(int n, const double* __restrict__ src, const int* __restrict__ perm,
+                                                        double* __restrict__ u0, double* __restrict__ u1, double* __restrict__ xrec,
+                                                        int64_t nxrec, LzPersistState* st) {
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u0[i] = src[perm[i]];
+        u1[i] = nanv;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxrec; i += (int64_t)gridDim.x * blockDim.x) xrec[i] = nanv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->phase = 0;
+        st->cur = 0;
+        st->k1 = 0.0; st->k2 = 1.0; st->k3 = 0.0; st->k4 = 0.0;
+        st->beta_prev = 0.0;
+        st->usum_prev = 0.0;
+        st->bar = 0u;
+    }
+}
+
+constexpr int kVecBatch = 8;   // gathers in flight per thread
+#ifdef MACB_DEBUG_VEC
+__device__ int g_dbg_count = 0;
+__device__ int g_prog[256];
+#define MACB_PROG(stage) do { if (tid == 0) { g_prog[blockIdx.x] = phase * 10 + (stage); } } while (0)
+#else
+#define MACB_PROG(stage) do {} while (0)
+#endif
+
+template <bool SORTED>
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJdsArgs J) {
+    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
+#define MACB_DST(cc, jj) (SORTED ? (((cc) >> 17) & 0x3fff) : (jj))
+    extern __shared__ double prod[];
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double tot[4];
+    __shared__ int stop_sm;
+    __shared__ int stop_in;
+    __shared__ int give_up;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
+    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
+    int* __restrict__ sjd = scol + J.prod_cap;
+    const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
+    const int sa = a.rp[ra], ns = a.rp[rb] - sa;
+    const bool has_row = tid < rb - ra;
+    const int row = ra + tid;
+    const int len = has_row ? J.jlen[row] : 0;
+    const double od = has_row ? J.diag[J.perm[row]] : 0.0;
+    const double* __restrict__ jval = J.jval + sa;
+    for (int i = tid; i < ns; i += kPBlock)
+        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
+    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
+    if (tid == 0) give_up = 0;
+
+    int phase = a.st->phase;
+    int cur = a.st->cur;
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed phase
+    double* const U0 = a.sect[0];
+    double* const U1 = a.sect[1];
+    // own rows: u_j and u_{j-1} live in registers for the whole launch
+    double su = 0.0, sq = 0.0;
+    if (has_row) {
+        su = __ldcg((cur ? U1 : U0) + row);
+        if (phase > 0) sq = __ldcg(a.basis + (size_t)(phase - 1) * a.ld + row);
+        else a.basis[row] = su;
+    }
+    __syncthreads();
+    const unsigned int ncta = (unsigned int)a.ncta;
+    const double inv_n = 1.0 / (double)a.n;
+    const int rows_warps = (rb - ra + 31) >> 5;
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+
+    for (int it = 0; it < a.nphases; ++it) {
+        const double* __restrict__ U = cur ? U1 : U0;
+        double* __restrict__ Un = cur ? U0 : U1;
+#ifdef MACB_PTIMING
+        long long t_start = clock64(), t_p1 = 0, t_coef = 0;
+#endif
+        if (blockIdx.x == 0 && tid == 0 && a.stop)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(&stop_in)), "l"(a.stop) : "memory");
+        MACB_PROG(1);
+        // ---- pass 1: products of the CTA's slots, kVecBatch gathers in flight per thread
+        for (int b0 = tid; b0 < ns; b0 += kVecBatch * kPBlock) {
+            int c[kVecBatch];
+            double v[kVecBatch];
+#pragma unroll
+            for (int q = 0; q < kVecBatch; ++q) {
+                const int b = b0 + q * kPBlock;
+                c[q] = (b < ns) ? scol[b] : (int)0x80000000;
+            }
+#pragma unroll
+            for (int q = 0; q < kVecBatch; ++q) v[q] = ld_f64_if(U + (c[q] & CM), c[q] >= 0);
+#pragma unroll
+            for (int q = 0; q < kVecBatch; ++q) {
+                const int b = b0 + q * kPBlock;
+                if (c[q] >= 0) {
+                    const double w = ld_nc(jval + b);
+                    if (v[q] != v[q]) {   // producer has not written yet: gather again (bounded: never hang the device)
+                        unsigned int tries = 0;
+                        do {
+                            v[q] = ld_f64_if(U + (c[q] & CM), true);
+                        } while (v[q] != v[q] && ++tries < (1u << 17));
+                        if (v[q] != v[q]) {
+                            give_up = 1;
+#ifdef MACB_DEBUG_VEC
+                            if (atomicAdd(&g_dbg_count, 1) < 3) {
+                                for (int z = 0; z < (int)gridDim.x; ++z) printf("[vec] prog cta %d = %d\n", z, *(volatile int*)&g_prog[z]);
+                            }
+                            if (atomicAdd(&g_dbg_count, 1) < 12)
+                                printf("[vec] t=%lld cta %d tid %d phase %d it %d: column %d of buffer %d still NaN\n", (long long)clock64(), (int)blockIdx.x, tid, phase, it, c[q] & CM, cur);
+#endif
+                        }
+                    }
+                    prod[MACB_DST(c[q], b)] = w * v[q];
+                } else if (b < ns) {
+                    prod[MACB_DST(c[q], b)] = 0.0;
+                }
+            }
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        t_p1 = clock64();
+#endif
+        MACB_PROG(2);
+        // ---- pass 2: row sums along the jagged diagonals, z_i, partial sums
+        double zr = 0.0;
+        if (warp < rows_warps) {
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+            if (has_row) {
+                const double* __restrict__ pt = prod + tid;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int d = 0;
+                for (; d + 4 <= len; d += 4) {
+                    const int4 o = *reinterpret_cast<const int4*>(sjd + d);
+                    a0 += pt[o.x];
+                    a1 += pt[o.y];
+                    a2 += pt[o.z];
+                    a3 += pt[o.w];
+                }
+                for (; d < len; ++d) a0 += pt[sjd[d]];
+                zr = fma(od, su, -((a0 + a1) + (a2 + a3)));   // (L u_phase)[row]
+                p1 = su * zr;
+                p2 = zr;
+                p3 = su * su;
+                p4 = su;
+            }
+            const double r = warp_sum4(p1, p2, p3, p4, lane);
+            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+        }
+        __syncthreads();
+#ifdef MACB_PTIMING
+        long long t_rows = clock64();
+        long long tb0 = 0, tb1 = 0, tb2 = 0, tb3 = 0;
+#endif
+        MACB_PROG(3);
+        // ---- barrier: all-to-all exchange of the partial sums (see k_lanczos_jds)
+        if (warp == 0) {
+            const double x0 = (lane < rows_warps) ? sm[lane] : 0.0, x1 = (lane < rows_warps) ? sm[kPWarps + lane] : 0.0,
+                         x2 = (lane < rows_warps) ? sm[2 * kPWarps + lane] : 0.0, x3 = (lane < rows_warps) ? sm[3 * kPWarps + lane] : 0.0;
+            const double r = warp_sum4(x0, x1, x2, x3, lane);
+            double q0 = __shfl_sync(0xffffffffu, r, 0), q1 = __shfl_sync(0xffffffffu, r, 8),
+                   q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
+            const double inf = __longlong_as_double(0x7ff0000000000000ll);
+            q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
+            if (*(volatile int*)&give_up) q0 = inf;   // poison alpha: the host sees a non-finite value and reports it
+            if (blockIdx.x == 0 && a.stop) {
+                int stop_now = 0;
+                if (lane == 0) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    stop_now = *(volatile int*)&stop_in;
+                }
+                if (__shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
+            }
+            double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
+#ifdef MACB_PTIMING
+            tb0 = clock64();
+#endif
+            __threadfence();
+#ifdef MACB_PTIMING
+            tb1 = clock64();
+#endif
+            for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
+            const double* const mine = box + (size_t)blockIdx.x * ncta * 4;
+            MACB_PROG(4);
+            double y0, y1, y2, y3;
+            int stop_seen;
+            unsigned int spins = 0;
+            while (true) {
+                bool ok = true;
+                y0 = y1 = y2 = y3 = 0.0;
+                stop_seen = 0;
+                for (unsigned int b = lane; b < ncta; b += 32) {
+                    double r0, r1, r2, r3;
+                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
+                    ok = ok && (r0 == r0) && (r1 == r1) && (r2 == r2) && (r3 == r3);
+                    if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
+                    y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > (1u << 18)) {
+#ifdef MACB_DEBUG_VEC
+                    if (lane == 0 && atomicAdd(&g_dbg_count, 1) < 12) printf("[vec] t=%lld cta %d phase %d: inbox incomplete\n", (long long)clock64(), (int)blockIdx.x, phase);
+#endif
+                    give_up = 1;
+                    break;
+                }
+            }
+#ifdef MACB_PTIMING
+            tb2 = clock64();
+#endif
+            const double t = warp_sum4(y0, y1, y2, y3, lane);
+            if ((lane & 7) == 0) tot[lane >> 3] = t;
+            if (lane == 0) stop_sm = stop_seen;
+            for (unsigned int b = lane; b < ncta; b += 32) st_sector(const_cast<double*>(mine) + (size_t)b * 4, nanv, nanv, nanv, nanv);
+#ifdef MACB_PTIMING
+            tb3 = clock64();
+#endif
+        }
+        __syncthreads();
+        MACB_PROG(5);
+        // ---- coefficients (every thread, identical arithmetic) and pass B: the CTA's rows of u_{phase+1}
+        const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
+        const int stop_all = stop_sm;
+        const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
+#ifdef MACB_PTIMING
+        t_coef = clock64();
+#endif
+        if (has_row) {
+            const double un = fma(cf.k1, zr, fma(cf.k2, su, cf.k3 * sq)) + cf.k4;
+#ifdef MACB_DEBUG_VEC
+            if (un != un && atomicAdd(&g_dbg_count, 1) < 12)
+                printf("[vec] cta %d row %d phase %d: u_next is NaN: zr %g su %g sq %g k %g %g %g %g P %g %g %g %g\n", (int)blockIdx.x, row, phase, zr, su, sq,
+                       cf.k1, cf.k2, cf.k3, cf.k4, P1, P2, P3, P4);
+#endif
+            __stcg(Un + row, un);
+            a.basis[(size_t)(phase + 1) * a.ld + row] = un;
+            __stcg(const_cast<double*>(U) + row, nanv);   // poison: this buffer is the target of phase + 1's pass B
+            sq = su;
+            su = un;
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            a.alpha[phase] = cf.alpha;
+            a.beta[phase] = cf.beta;
+            if (a.ab_host)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(cf.alpha), "d"(cf.beta) : "memory");
+        }
+        beta_prev = cf.binv;
+        usum_prev = P4;
+        MACB_PROG(6);
+#ifdef MACB_PTIMING
+        if (tid == 0 && a.timing && it < 64) {
+            long long* e = a.timing + (size_t)64 * a.ncta * 5 + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            e[0] = tb0; e[1] = tb1; e[2] = tb2; e[3] = tb3;
+            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
+            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = t_coef;
+            a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
+        }
+#endif
+        cur ^= 1;
+        ++phase;
+        if (stop_all) break;
+    }
+#undef MACB_DST
+    if (blockIdx.x == 0 && tid == 0) {
+        a.st->phase = phase;
+        a.st->cur = cur;
+        a.st->beta_prev = beta_prev;
+        a.st->usum_prev = usum_prev;
+    }
+}
 
 // ---- K3, single-CTA form for small graphs (pose graphs with n up to 3072 nodes, 12288 slots) -------------
 // When 24 n + 16 nnz bytes fit in one SM's shared memory the whole problem lives on that SM: (z, u, u') per
