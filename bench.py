@@ -254,17 +254,18 @@ def run_ours(args, rank, local_rank, world):
                 "api": "MAC.frank_wolfe(k, x_init, max_iters=K) -> macb_fw_run, host numpy buffers"},
         "gpu_launches": counters["kernel_launches"],
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_lanczos_slots: one launch per eigen-solve, one SpMV-with-fused-recurrence + "
-                     "one grid barrier per Lanczos step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": f"{h.lanczos_kernel_name()}: one launch per eigen-solve; per Lanczos step one SpMV "
+                     "(8-byte gathers from the materialised Lanczos vector, slots in column order), row sums, ONE grid barrier "
+                     "(all-to-all exchange of the partial sums) and a local three-term update", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "us_per_lanczos_step": lz_us, "lanczos_steps_timed": lz["phases"],
                      "share_of_timed_region": lz["ms"] / (dev_max * 1e3),
                      "algorithmic_bytes_per_step": lz["algo_bytes_per_phase"],
                      "standalone_spmv": {"kernel": "k_spmv", "achieved": spmv_achieved, "frac": spmv_achieved / peak},
                      "note": "achieved = algorithmic bytes per Lanczos step x steps / CUDA-event time of the kernel launches inside "
-                             "the timed region. The 29.6 MB matrix is L2-resident and the access pattern is one random 32-byte "
-                             "sector per non-zero, so the binding limit is the L1TEX divergent-gather rate (measured ceiling 0.9 "
-                             "sector/clk/SM, tools/micro/gather_mix.cu), not HBM: see DESIGN.md section 5"},
+                             "the timed region. The 29.6 MB matrix is L2-resident (traffic = measured DRAM bytes per step) and the "
+                             "access pattern is one random gather per non-zero, so the binding limit is the L1TEX wavefront rate "
+                             "(one 128-byte line per clock and SM, tools/micro/gather_mix.cu), not HBM: see DESIGN.md section 5"},
     }
     if world == 1 and not args.no_cpu_baseline:
         fixed0, cand0, n0, k0, x00 = (fixed, cand, n, k, x0)

@@ -152,6 +152,11 @@ int macb_iter_ms(macb_handle h, double* ms, int cap, int* count);
  * bytes of one step.  This is the dominant kernel of the path; bench.py derives its roofline line from it. */
 int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double* algo_bytes_per_phase);
 
+/* Name of the Lanczos kernel this handle launches (chosen from the graph's size at the first eigen-solve):
+ * "k_lanczos_vec", "k_lanczos_jds", "k_lanczos_slots", "k_lanczos_small", "k_lanczos_persist" or "k_spmv+k_lanczos_b"
+ * (CUDA-graph engine); "" before the first solve.  The pointer stays valid for the life of the handle. */
+const char* macb_lanczos_kernel_name(macb_handle h);
+
 /* cudaDeviceSynchronize on the handle's device. */
 int macb_device_sync(macb_handle h);
 

@@ -75,6 +75,7 @@ def lib():
     _sig(L.macb_iter_ms, [H, _dp, C.c_int, C.POINTER(C.c_int)])
     _sig(L.macb_device_sync, [H])
     _sig(L.macb_lanczos_kernel_time, [H, _dp, _lp, _dp])
+    _sig(L.macb_lanczos_kernel_name, [H], C.c_char_p)
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_version, [], C.c_char_p)
@@ -248,6 +249,9 @@ class Handle:
         ms, by, ph = C.c_double(), C.c_double(), C.c_int64()
         self._L.macb_lanczos_kernel_time(self._h, C.byref(ms), C.byref(ph), C.byref(by))
         return {"ms": ms.value, "phases": ph.value, "algo_bytes_per_phase": by.value}
+
+    def lanczos_kernel_name(self):
+        return self._L.macb_lanczos_kernel_name(self._h).decode()
 
     def device_sync(self):
         self._check(self._L.macb_device_sync(self._h), "macb_device_sync")

@@ -1533,10 +1533,26 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
     if (!h) return MACB_ERR_ARG;
     if (ms) *ms = h->lz_kernel_ms;
     if (phases) *phases = h->lz_kernel_phases;
-    // one Lanczos phase = one SpMV + the 32-byte state sector and the 8-byte basis entry per node
-    if (algo_bytes_per_phase)
-        *algo_bytes_per_phase = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n + 40.0 * (double)h->n;
+    // one Lanczos phase = one SpMV ((nnz + n) * 12 + 4 (n + 1) + 16 n) plus what the engine writes per node:
+    // the 32-byte state sector and the 8-byte basis entry (sector engines), or the new vector entry, the basis entry
+    // and the poison word (k_lanczos_vec)
+    if (algo_bytes_per_phase) {
+        const double spmv = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n;
+        const bool vec = h->persist && h->persist_v == 5 && h->jds_vec;
+        *algo_bytes_per_phase = spmv + (vec ? 24.0 : 40.0) * (double)h->n;
+    }
     return MACB_OK;
+}
+
+const char* macb_lanczos_kernel_name(macb_handle h) {
+    if (!h || !h->d_basis) return "";
+    if (!h->persist) return "k_spmv+k_lanczos_b";
+    switch (h->persist_v) {
+        case 5: return h->jds_vec ? "k_lanczos_vec" : "k_lanczos_jds";
+        case 4: return "k_lanczos_small";
+        case 3: return "k_lanczos_slots";
+        default: return "k_lanczos_persist";
+    }
 }
 
 int macb_device_sync(macb_handle h) {

@@ -1209,7 +1209,10 @@ __global__ void __launch_bounds__(kBlock) k_lz_vec_init(int n, const double* __r
     }
 }
 
-constexpr int kVecBatch = 8;   // gathers in flight per thread
+#ifndef MACB_VEC_BATCH
+#define MACB_VEC_BATCH 8
+#endif
+constexpr int kVecBatch = MACB_VEC_BATCH;   // gathers in flight per thread
 #ifdef MACB_DEBUG_VEC
 __device__ int g_dbg_count = 0;
 __device__ int g_prog[256];
