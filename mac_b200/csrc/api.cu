@@ -536,8 +536,43 @@ void setup_persist(macb_ctx* c) {
                         std::sort(key.begin(), key.end());
                         tc.resize(ns);
                         te.resize(ns);
+                        // Which diagonal a slot's product goes to is free within its row (pass 2 sums all of them).  A
+                        // half-warp stores 16 products of 8 bytes: conflict-free iff their positions differ mod 16.  Walk
+                        // the column-sorted slots in groups of 16 and give every slot a still unused diagonal of its row
+                        // whose position falls into a bank the group has not used yet (first fit; any free one otherwise).
+                        const int R = rs[b + 1] - rs[b];
+                        const int* jdb = jd.data() + (size_t)b * stride;
+                        std::vector<int> pos_row((size_t)ns), newpos((size_t)ns);
+                        std::vector<std::vector<unsigned char>> used_d((size_t)R);
+                        for (int t = 0; t < R; ++t) {
+                            const int len = jlen[rs[b] + t];
+                            used_d[t].assign((size_t)len, 0);
+                            for (int d = 0; d < len; ++d) pos_row[(size_t)jdb[d] + t] = t;
+                        }
+                        const bool avoid = !getenv("MACB_NO_BANKFIT");
+                        for (int g0 = 0; g0 < ns; g0 += 16) {
+                            unsigned int banks = 0;
+                            for (int q = g0; q < std::min(ns, g0 + 16); ++q) {
+                                const int t = pos_row[key[q].second];
+                                std::vector<unsigned char>& u = used_d[t];
+                                int pick = -1, fallback = -1;
+                                for (int d = 0; d < (int)u.size(); ++d) {
+                                    if (u[d]) continue;
+                                    if (fallback < 0) fallback = d;
+                                    if (!avoid) break;
+                                    if (!((banks >> ((jdb[d] + t) & 15)) & 1u)) {
+                                        pick = d;
+                                        break;
+                                    }
+                                }
+                                if (pick < 0) pick = fallback;
+                                u[pick] = 1;
+                                banks |= 1u << ((jdb[pick] + t) & 15);
+                                newpos[q] = jdb[pick] + t;
+                            }
+                        }
                         for (int q = 0; q < ns; ++q) {
-                            tc[q] = key[q].first | (key[q].second << 17);
+                            tc[q] = key[q].first | (newpos[q] << 17);
                             te[q] = jeid[(size_t)sa + key[q].second];
                         }
                         std::copy(tc.begin(), tc.end(), jcol.begin() + sa);

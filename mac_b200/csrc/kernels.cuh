@@ -1317,6 +1317,11 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
 #endif
         MACB_PROG(2);
         // ---- pass 2: row sums along the jagged diagonals, z_i, partial sums
+        // The release fence of the record exchange (it orders the CTA's pass-B stores of the previous phase -- vector
+        // entries and poison -- before the record this CTA is about to push) is executed here by the last warp, which
+        // has no rows unless the CTA has more than 992: it overlaps with the row sums instead of sitting on warp 0's
+        // critical path.  fence (warp 31) -> __syncthreads -> push (warp 0) is a release sequence through the barrier.
+        if (warp == kPWarps - 1) __threadfence();
         double zr = 0.0;
         if (warp < rows_warps) {
             double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
@@ -1368,10 +1373,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
             double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
 #ifdef MACB_PTIMING
             tb0 = clock64();
-#endif
-            __threadfence();
-#ifdef MACB_PTIMING
-            tb1 = clock64();
+            tb1 = tb0;
 #endif
             for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
             const double* const mine = box + (size_t)blockIdx.x * ncta * 4;
