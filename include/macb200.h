@@ -152,6 +152,12 @@ int macb_iter_ms(macb_handle h, double* ms, int cap, int* count);
  * bytes of one step.  This is the dominant kernel of the path; bench.py derives its roofline line from it. */
 int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double* algo_bytes_per_phase);
 
+/* Selects the kernel behind macb_spmv / macb_spmv_bench: 0 = k_spmv (CSR, W lanes per row; default), 1 = k_spmv_jds (chunked
+ * jagged-diagonal layout with column-sorted slots, built on first use; for matrices far larger than L2 with locality it is bound
+ * by HBM instead of by the gather rate).  Same result up to the order of summation inside a row.  Replaces the same site as
+ * macb_spmv (`L @ X`, nx:237). */
+int macb_spmv_engine(macb_handle h, int engine);
+
 /* Name of the Lanczos kernel this handle launches (chosen from the graph's size at the first eigen-solve):
  * "k_lanczos_vec", "k_lanczos_jds", "k_lanczos_slots", "k_lanczos_small", "k_lanczos_persist" or "k_spmv+k_lanczos_b"
  * (CUDA-graph engine); "" before the first solve.  The pointer stays valid for the life of the handle. */

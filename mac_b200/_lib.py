@@ -76,6 +76,7 @@ def lib():
     _sig(L.macb_device_sync, [H])
     _sig(L.macb_lanczos_kernel_time, [H, _dp, _lp, _dp])
     _sig(L.macb_lanczos_kernel_name, [H], C.c_char_p)
+    _sig(L.macb_spmv_engine, [H, C.c_int])
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_version, [], C.c_char_p)
@@ -249,6 +250,10 @@ class Handle:
         ms, by, ph = C.c_double(), C.c_double(), C.c_int64()
         self._L.macb_lanczos_kernel_time(self._h, C.byref(ms), C.byref(ph), C.byref(by))
         return {"ms": ms.value, "phases": ph.value, "algo_bytes_per_phase": by.value}
+
+    def spmv_engine(self, engine):
+        """0: CSR kernel (default); 1: chunked jagged-diagonal kernel (built on first use)."""
+        self._check(self._L.macb_spmv_engine(self._h, int(engine)), "macb_spmv_engine")
 
     def lanczos_kernel_name(self):
         return self._L.macb_lanczos_kernel_name(self._h).decode()

@@ -90,6 +90,15 @@ struct macb_ctx {
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool jds_sorted = false;
+    // chunked jagged-diagonal SpMV (k_spmv_jds): built on demand by macb_spmv_engine(h, 1)
+    int spmv_engine = 0;           // 0: k_spmv (CSR, W lanes per row), 1: k_spmv_jds
+    int sj_nchunks = 0;
+    int *d_sj_chunk_row = nullptr, *d_sj_chunk_jd = nullptr, *d_sj_jd = nullptr, *d_sj_perm = nullptr, *d_sj_len = nullptr,
+        *d_sj_eid = nullptr, *d_sj_col0 = nullptr, *d_sj_col = nullptr;
+    unsigned int* d_sj_word = nullptr;
+    bool sj_col16 = false;
+    int64_t* d_sj_chunk_slot = nullptr;
+    double* d_sj_val = nullptr;
     bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
@@ -252,7 +261,8 @@ void free_all(macb_ctx* c) {
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
                      c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
-                     c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec};
+                     c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec, c->d_sj_chunk_row, c->d_sj_chunk_jd, c->d_sj_jd,
+                     c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
@@ -320,6 +330,10 @@ void launch_assemble(macb_ctx* c) {
         k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
         c->c_launches++;
     }
+    if (c->d_sj_val) {
+        k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_sj_eid, c->d_ew, c->d_sj_val);
+        c->c_launches++;
+    }
     CK(cudaGetLastError());
     c->c_launches++;
     CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -347,6 +361,15 @@ void launch_spmv(macb_ctx* c, const double* x, double* y) {
     a.beta = c->d_beta;
     a.ysum = c->d_ysum;
     a.ws = c->ws();
+    if (MODE == 0 && c->spmv_engine == 1 && c->d_sj_val) {
+        SpmvJdsArgs j{c->sj_nchunks, c->d_sj_chunk_row, c->d_sj_chunk_slot, c->d_sj_chunk_jd, c->d_sj_col0, c->d_sj_jd, c->d_sj_perm,
+                      c->d_sj_len, c->d_sj_word, c->d_sj_col, c->d_sj_val, c->d_diag, x, y};
+        const int grid = std::min(c->sj_nchunks, 4 * c->sm_count);
+        if (c->sj_col16) k_spmv_jds<true><<<grid, kSjBlock, 0, c->stream>>>(j);
+        else k_spmv_jds<false><<<grid, kSjBlock, 0, c->stream>>>(j);
+        CK(cudaGetLastError());
+        return;
+    }
     const int grid = c->grid_rows();
     DISPATCH_W(c->W, k_spmv<WW, MODE><<<grid, kBlock, 0, c->stream>>>(a));
     CK(cudaGetLastError());
@@ -1593,6 +1616,121 @@ const char* macb_lanczos_kernel_name(macb_handle h) {
 int macb_device_sync(macb_handle h) {
     return guarded(h, [&]() {
         CK(cudaDeviceSynchronize());
+        return (int)MACB_OK;
+    });
+}
+
+// Builds the chunked jagged-diagonal copy of the pattern for k_spmv_jds (kernels.cuh).  Returns false when a row is
+// longer than a chunk can hold (the CSR kernel then stays in charge).
+static bool build_spmv_jds(macb_ctx* c) {
+    const int n = c->n;
+    const int64_t nnz = c->nnz;
+    std::vector<int> col((size_t)nnz), eid((size_t)nnz);
+    if (nnz) {
+        CK(cudaMemcpy(col.data(), c->d_col, sizeof(int) * nnz, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(eid.data(), c->d_eid, sizeof(int) * nnz, cudaMemcpyDeviceToHost));
+    }
+    const std::vector<int32_t>& rp = c->h_rp;
+    // pass A: chunk boundaries; can every chunk use 16-bit column offsets?
+    std::vector<int> chunk_row{0};
+    std::vector<int64_t> chunk_slot{0};
+    bool col16 = !getenv("MACB_SPMV_COL32");
+    for (int r = 0; r < n;) {
+        int e = r;
+        while (e < n && e - r < kSjRows && (int64_t)rp[e + 1] - rp[r] <= kSjCap) ++e;
+        if (e == r) return false;   // a single row exceeds the chunk capacity
+        int cmin = std::numeric_limits<int>::max(), cmax = 0;
+        for (int64_t s = rp[r]; s < rp[e]; ++s) {
+            cmin = std::min(cmin, col[(size_t)s]);
+            cmax = std::max(cmax, col[(size_t)s]);
+        }
+        if (rp[e] > rp[r] && cmax - cmin > 65535) col16 = false;
+        chunk_row.push_back(e);
+        chunk_slot.push_back(rp[e]);
+        r = e;
+    }
+    const int nchunks = (int)chunk_row.size() - 1;
+    std::vector<int> chunk_jd{0}, chunk_col0((size_t)nchunks, 0), jd, perm((size_t)n), len((size_t)n), jeid((size_t)nnz, 0);
+    std::vector<int> jcol32(col16 ? 0 : (size_t)nnz, 0);
+    std::vector<unsigned int> word((size_t)nnz, 0u);
+    std::vector<int> order, cnt, base, pos2eid;
+    std::vector<std::pair<int, int>> key;
+    for (int q = 0; q < nchunks; ++q) {
+        const int r = chunk_row[q], e = chunk_row[q + 1], R = e - r;
+        const int ns = (int)(rp[e] - rp[r]);
+        const int64_t s0 = chunk_slot[q];
+        order.resize(R);
+        for (int t = 0; t < R; ++t) order[t] = r + t;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
+        const int maxlen = R ? rp[order[0] + 1] - rp[order[0]] : 0;
+        if (maxlen > kSjMaxLen) return false;
+        cnt.assign((size_t)maxlen + 1, 0);
+        for (int t = 0; t < R; ++t) {
+            perm[r + t] = order[t];
+            len[r + t] = rp[order[t] + 1] - rp[order[t]];
+            for (int d = 0; d < len[r + t]; ++d) cnt[d]++;
+        }
+        base.assign((size_t)maxlen + 1, 0);
+        for (int d = 1; d <= maxlen; ++d) base[d] = base[d - 1] + cnt[d - 1];
+        for (int d = 0; d <= maxlen; ++d) jd.push_back(base[d]);
+        chunk_jd.push_back((int)jd.size());
+        key.clear();
+        pos2eid.assign((size_t)std::max(ns, 1), 0);
+        int cmin = std::numeric_limits<int>::max();
+        for (int t = 0; t < R; ++t) {
+            const int row = order[t];
+            for (int d = 0; d < len[r + t]; ++d) {
+                const int cc = col[(size_t)rp[row] + d];
+                key.push_back({cc, base[d] + t});
+                pos2eid[(size_t)base[d] + t] = eid[(size_t)rp[row] + d];
+                cmin = std::min(cmin, cc);
+            }
+        }
+        if (ns == 0) cmin = 0;
+        chunk_col0[q] = cmin;
+        std::sort(key.begin(), key.end());
+        for (int p = 0; p < ns; ++p) {
+            if (col16) {
+                word[(size_t)s0 + p] = (unsigned int)(key[p].first - cmin) | ((unsigned int)key[p].second << 16);
+            } else {
+                jcol32[(size_t)s0 + p] = key[p].first;
+                word[(size_t)s0 + p] = (unsigned int)key[p].second;
+            }
+            jeid[(size_t)s0 + p] = pos2eid[(size_t)key[p].second];
+        }
+    }
+    c->sj_nchunks = nchunks;
+    c->sj_col16 = col16;
+    auto up = [&](auto*& dptr, const auto& v) {
+        using T = typename std::remove_const<typename std::remove_reference<decltype(v[0])>::type>::type;
+        dptr = dalloc<T>(v.size());
+        if (!v.empty()) CK(cudaMemcpy(dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    };
+    up(c->d_sj_chunk_row, chunk_row);
+    up(c->d_sj_chunk_slot, chunk_slot);
+    up(c->d_sj_chunk_jd, chunk_jd);
+    up(c->d_sj_col0, chunk_col0);
+    up(c->d_sj_jd, jd);
+    up(c->d_sj_perm, perm);
+    up(c->d_sj_len, len);
+    up(c->d_sj_eid, jeid);
+    up(c->d_sj_word, word);
+    if (!col16) up(c->d_sj_col, jcol32);
+    c->d_sj_val = dalloc<double>((size_t)nnz);
+    if (c->have_x) {
+        k_assemble_jds<<<c->grid_for(nnz), kBlock, 0, c->stream>>>(nnz, c->d_sj_eid, c->d_ew, c->d_sj_val);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return true;
+}
+
+int macb_spmv_engine(macb_handle h, int engine) {
+    return guarded(h, [&]() {
+        if (engine != 0 && engine != 1) throw ArgFail{"macb_spmv_engine: engine must be 0 (CSR) or 1 (chunked jagged-diagonal)", MACB_ERR_ARG};
+        if (engine == 1 && !h->d_sj_val && !build_spmv_jds(h))
+            throw ArgFail{"macb_spmv_engine: a row is longer than a chunk of the jagged-diagonal kernel", MACB_ERR_ARG};
+        h->spmv_engine = engine;
         return (int)MACB_OK;
     });
 }

@@ -274,6 +274,110 @@ __global__ void __launch_bounds__(kBlock) k_spmv(SpmvArgs a) {
     }
 }
 
+// ---- K1, chunked jagged-diagonal form (HBM-bound matrices) -----------------------------------------------------
+// k_spmv above spends one L1TEX wavefront per non-zero on the gather of x (32 lanes, 32 different 128-byte lines) and is
+// therefore bound by the SM's memory front end (~0.9 nnz/clk/SM = 3.1 TB/s of matrix stream), not by HBM.  Here the
+// matrix is cut into chunks of <= kSjRows rows / <= kSjCap slots; inside a chunk the slots are stored in COLUMN order,
+// so that on matrices with locality (pose graphs: |i - j| bounded) the 32 lanes of a gather share one or two lines, and
+// every slot carries the position of its product in the chunk's jagged-diagonal buffer (rows sorted by decreasing length,
+// diagonal d = the d-th product of every row that has one):
+//   pass 1   prod[pos_s] = val_s * x[col_s]     coalesced streams: one 32-bit word (16-bit column offset | 16-bit position)
+//            + the weight = 12 bytes per slot when the chunk's columns span < 65536, 14 bytes (32-bit column) otherwise;
+//            eight slots in flight per thread
+//   pass 2   y[row_t] = diag * x[row_t] - sum_d prod[jd[d] + t]      conflict-free shared-memory reads
+// Four CTAs per SM so that one CTA's streams overlap the other's row sums.  (Staging whole chunks through the TMA unit
+// -- cp.async.bulk + mbarrier, one chunk ahead -- was measured slower: the stream was never the problem, the serial
+// pass 1 -> pass 2 structure of a single resident CTA is.)
+constexpr int kSjBlock = 256;
+constexpr int kSjRows = 256;
+constexpr int kSjCap = 2048;     // slots per chunk: 16 KB of products
+constexpr int kSjMaxLen = 1023;  // longest row a chunk can hold (its diagonal starts live in shared memory)
+constexpr int kSjBatch = 8;
+
+struct SpmvJdsArgs {
+    int nchunks;
+    const int* chunk_row;       // [nchunks + 1] first (chunk-ordered) row of every chunk
+    const int64_t* chunk_slot;  // [nchunks + 1] first slot
+    const int* chunk_jd;        // [nchunks + 1] first entry of the chunk's diagonal starts in jd
+    const int* chunk_col0;      // [nchunks] smallest column of the chunk (COL16: col = col0 + low 16 bits)
+    const int* jd;
+    const int* perm;            // [n] chunk-ordered row -> row of the caller
+    const int* len;             // [n] its number of slots
+    const unsigned int* word;   // [slots] COL16: column offset | position << 16;  else: position
+    const int* col;             // [slots] 32-bit column (!COL16 only)
+    const double* val;          // [slots]
+    const double* diag;         // [n] caller numbering
+    const double* x;
+    double* y;
+};
+
+__device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) {
+    unsigned int r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+template <bool COL16>
+__global__ void __launch_bounds__(kSjBlock, 4) k_spmv_jds(SpmvJdsArgs a) {
+    __shared__ double prod[kSjCap];
+    __shared__ int sjd[kSjMaxLen + 1];
+    const int tid = (int)threadIdx.x;
+    for (int q = blockIdx.x; q < a.nchunks; q += gridDim.x) {
+        const int r0 = a.chunk_row[q], nrows = a.chunk_row[q + 1] - r0;
+        const int64_t s0 = a.chunk_slot[q];
+        const int ns = (int)(a.chunk_slot[q + 1] - s0);
+        const int j0 = a.chunk_jd[q], nj = a.chunk_jd[q + 1] - j0;
+        const int col0 = COL16 ? a.chunk_col0[q] : 0;
+        for (int i = tid; i < nj; i += kSjBlock) sjd[i] = a.jd[j0 + i];
+        int row = 0, len = 0;
+        double dxr = 0.0;
+        if (tid < nrows) {
+            row = a.perm[r0 + tid];
+            len = a.len[r0 + tid];
+            dxr = a.diag[row] * ld_nc(a.x + row);
+        }
+        const unsigned int* __restrict__ word = a.word + s0;
+        const int* __restrict__ col = a.col + s0;
+        const double* __restrict__ val = a.val + s0;
+        for (int b0 = tid; b0 < ns; b0 += kSjBatch * kSjBlock) {
+            unsigned int w[kSjBatch];
+            int c[kSjBatch];
+            double v[kSjBatch], xv[kSjBatch];
+#pragma unroll
+            for (int k = 0; k < kSjBatch; ++k) {
+                const int b = b0 + k * kSjBlock;
+                w[k] = (b < ns) ? ld_stream(word + b) : 0u;
+                c[k] = COL16 ? col0 + (int)(w[k] & 0xffffu) : ((b < ns) ? ld_stream(col + b) : 0);
+            }
+#pragma unroll
+            for (int k = 0; k < kSjBatch; ++k) {
+                const int b = b0 + k * kSjBlock;
+                v[k] = (b < ns) ? ld_stream(val + b) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < kSjBatch; ++k) xv[k] = ld_nc(a.x + c[k]);
+#pragma unroll
+            for (int k = 0; k < kSjBatch; ++k) {
+                const int b = b0 + k * kSjBlock;
+                if (b < ns) prod[COL16 ? (w[k] >> 16) : w[k]] = v[k] * xv[k];
+            }
+        }
+        __syncthreads();
+        if (tid < nrows) {
+            const double* __restrict__ pt = prod + tid;
+            double a0 = 0.0, a1 = 0.0;
+            int d = 0;
+            for (; d + 2 <= len; d += 2) {
+                a0 += pt[sjd[d]];
+                a1 += pt[sjd[d + 1]];
+            }
+            if (d < len) a0 += pt[sjd[d]];
+            a.y[row] = dxr - (a0 + a1);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- K3: Lanczos B-step ---------------------------------------------------------------------------
 // u_{j+1} = y - alpha_j v_j - beta_j v_{j-1} - c 1 ;  beta_{j+1} = ||u_{j+1}|| ; step = j + 1
 // Three-term recurrence of the operator P L P, P = I - 11^T/n: the projection the reference applies

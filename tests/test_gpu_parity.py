@@ -74,6 +74,11 @@ def test_spmv_and_assembly_match_scipy(case):
         assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
         assert abs(h.lnorm() - abs(L).sum(axis=1).max()) <= 1e-12 * max(1.0, h.lnorm())
         assert np.allclose(h.get_x(), x, rtol=0, atol=0)
+        # the chunked jagged-diagonal SpMV (HBM-bound matrices) sums a row in a different order: same result to rounding
+        h.spmv_engine(1)
+        y2 = h.spmv(v)
+        h.spmv_engine(0)
+        assert np.abs(y2 - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
     assert h.sizes()["nnz_union"] == 2 * (np.sum(fixed[0] != fixed[1]) + np.sum(cand[0] != cand[1]))
     h.close()
 
@@ -167,13 +172,15 @@ def test_warm_start_reaches_the_same_pair():
     mac.close()
 
 
-@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"}, {"MACB_JDS_SORT": "0"},
+@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"}, {"MACB_JDS_SORT": "0"}, {"MACB_NO_VEC": "1"},
+                                 {"MACB_NO_VEC": "1", "MACB_JDS_SORT": "0"},
                                  {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
                                  {"MACB_PERSIST_V": "1", "MACB_ASYNC": "0", "MACB_PERSIST_STREAM": "1"}])
 def test_lanczos_engines_agree(monkeypatch, env):
-    """The default engine (slot-parallel persistent kernel with jagged-diagonal staging + asynchronous host
-    Rayleigh-Ritz) against the alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel persistent
-    kernel, synchronous batches, CSR-ordered slot kernel with and without the shared-memory column cache."""
+    """The default engine (k_lanczos_vec: materialised Lanczos vector, column-sorted slots, jagged-diagonal staging,
+    asynchronous host Rayleigh-Ritz) against the alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel
+    persistent kernel, synchronous batches, CSR-ordered slot kernel with and without the shared-memory column cache,
+    jagged-diagonal kernels without column sorting, 32-byte-sector kernel k_lanczos_jds."""
     fixed, cand, n = synth.chain_plus_random(4000, 40000, seed=3, weighted=True)
     x = synth.first_k_init(40000, 8000)
     ref = MAC(fixed, cand, n)
