@@ -1388,11 +1388,16 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
             }
 #pragma unroll
             for (int q = 0; q < kVecBatch; ++q) v[q] = ld_f64_if(U + (c[q] & CM), c[q] >= 0);
+            // the weights of the whole batch are requested up front as well: loaded one by one next to their use they
+            // form a chain of kVecBatch dependent L2 latencies per batch
+            double wq[kVecBatch];
+#pragma unroll
+            for (int q = 0; q < kVecBatch; ++q) wq[q] = (c[q] >= 0) ? ld_stream(jval + b0 + q * kPBlock) : 0.0;
 #pragma unroll
             for (int q = 0; q < kVecBatch; ++q) {
                 const int b = b0 + q * kPBlock;
                 if (c[q] >= 0) {
-                    const double w = ld_nc(jval + b);
+                    const double w = wq[q];
                     if (v[q] != v[q]) {   // producer has not written yet: gather again (bounded: never hang the device)
                         unsigned int tries = 0;
                         do {
