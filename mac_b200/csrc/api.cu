@@ -846,7 +846,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                     fprintf(stderr, "[macb] k=%d checks=%d wait=%.0fus rr=%.0fus stop->sync=%.0fus t=%.0fus\n", k, n_checks, t_wait, t_rr,
                             us() - ts0, us());
                 const int phases_before = phases_done;
-                CK(cudaMemcpy(&phases_done, &c->d_pst->phase, sizeof(int), cudaMemcpyDeviceToHost));
+                phases_done = ((volatile int*)c->h_stop)[1];   // written by the kernel at exit (host-mapped)
                 c->ab_dirty = std::max(c->ab_dirty, phases_done);
                 if (c->bench_time_iters) {
                     float ms = 0.f;
@@ -1045,7 +1045,10 @@ void launch_gradient(macb_ctx* c) {
 }
 
 // radix-select passes over `g` (device, length m) + selection mask into `sel`; dual term into sc
-void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel, SelState* st = nullptr) {
+// defer = true: the "are there ties at the k-th value" decision (which needs the selection state on the host) is not
+// taken here: the tie-free apply kernel is enqueued speculatively and the caller, after its own synchronisation, calls
+// topk_fixup(), which re-runs the ranked path in the rare case that ties straddle the budget.
+void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel, SelState* st = nullptr, bool defer = false) {
     if (!st) st = c->d_sel_state;
     PhaseTimer pt(c, MACB_T_TOPK);
     const int64_t m = c->m;
@@ -1061,10 +1064,16 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_sel_state, st, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
     int64_t chunk = (m + grid - 1) / grid;
     chunk = ((chunk + kBlock - 1) / kBlock) * kBlock;
     const int nblocks = (int)((m + chunk - 1) / chunk);
+    if (defer) {
+        k_sel_apply<false><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, st, c->d_blockcnt, sel, c->d_sc, c->ws());
+        c->c_launches += 1;
+        CK(cudaGetLastError());
+        return;
+    }
+    CK(cudaStreamSynchronize(c->stream));
     const bool ranked = k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining;
     if (ranked) {
         k_sel_tie_count<<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, st, c->d_blockcnt);
@@ -1076,6 +1085,24 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
         c->c_launches += 1;
     }
     CK(cudaGetLastError());
+}
+
+// After a deferred launch_topk and a stream synchronisation: true (and the ranked selection re-done, synchronised) when
+// ties at the k-th value straddle the budget.
+bool topk_fixup(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel, SelState* st = nullptr) {
+    if (!st) st = c->d_sel_state;
+    if (!(k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining)) return false;
+    const int64_t m = c->m;
+    const int grid = c->grid_for(m);
+    int64_t chunk = (m + grid - 1) / grid;
+    chunk = ((chunk + kBlock - 1) / kBlock) * kBlock;
+    const int nblocks = (int)((m + chunk - 1) / chunk);
+    k_sel_tie_count<<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, st, c->d_blockcnt);
+    k_sel_tie_scan<<<1, 32, 0, c->stream>>>(nblocks, c->d_blockcnt);
+    k_sel_apply<true><<<nblocks, kBlock, 0, c->stream>>>(m, chunk, g, x, st, c->d_blockcnt, sel, c->d_sc, c->ws());
+    c->c_launches += 3;
+    CK(cudaGetLastError());
+    return true;
 }
 
 void set_x_device(macb_ctx* c, double tol) {
@@ -1473,9 +1500,13 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
             int rc = run_fiedler(h, fiedler_tol, fiedler_max_steps, warm && it > 0, fr);
             if (rc == MACB_NOT_CONVERGED) status = MACB_NOT_CONVERGED;
             launch_gradient(h);  // g                             mac.py:117-124
-            launch_topk(h, h->d_g, h->d_x, k, h->d_sel);  // s    frankwolfe.py:58
+            launch_topk(h, h->d_g, h->d_x, k, h->d_sel, nullptr, true);  // s    frankwolfe.py:58
             CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
+            if (topk_fixup(h, h->d_g, h->d_x, k, h->d_sel)) {   // ties at the k-th value: lowest index first
+                CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
             const double f = fr.lambda2;
             u = std::min(u, f + h->h_sc->gs_minus_x);  //         frankwolfe.py:62
             if (f_hist) f_hist[it] = f;

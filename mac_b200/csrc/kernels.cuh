@@ -701,6 +701,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = cur;
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = beta_prev;
@@ -942,6 +943,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = cur;
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = beta_prev;
@@ -1263,6 +1265,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = cur;
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = carry[phase & 1][0];
@@ -1569,6 +1572,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
 #undef MACB_DST
     if (blockIdx.x == 0 && tid == 0) {
         a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = cur;
         a.st->beta_prev = beta_prev;
         a.st->usum_prev = usum_prev;
@@ -1740,6 +1744,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, c
         st_sector(G + 4 * (size_t)i, sec[3 * i], sec[3 * i + 1], sec[3 * i + 2], diag[i]);
     if (threadIdx.x == 0) {
         a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = 0;
         a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
         a.st->beta_prev = beta_prev;
@@ -1780,14 +1785,15 @@ __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const dou
     __shared__ int flag;
     double r0 = 0.0, r1 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        int t = 0;
-        for (; t + 4 <= k; t += 4) {
+        // newest vectors first: the last ~100 MB the Lanczos kernel wrote are still in L2
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int t = k;
+        for (; t >= 8; t -= 8) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = fma(coef[t + q], basis[(size_t)(t + q) * ld + i], acc[q]);
+            for (int q = 0; q < 8; ++q) acc[q] = fma(coef[t - 1 - q], basis[(size_t)(t - 1 - q) * ld + i], acc[q]);
         }
-        for (; t < k; ++t) acc[0] = fma(coef[t], basis[(size_t)t * ld + i], acc[0]);
-        double yv = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        for (; t > 0; --t) acc[0] = fma(coef[t - 1], basis[(size_t)(t - 1) * ld + i], acc[0]);
+        double yv = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
         out[perm ? perm[i] : i] = yv;
         r0 += yv;
         r1 = fma(yv, yv, r1);
