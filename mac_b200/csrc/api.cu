@@ -504,8 +504,8 @@ void setup_persist(macb_ctx* c) {
             }
             CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
             // jagged-diagonal staging (k_lanczos_jds): one chunk per CTA, products + column cache + diagonal starts fit
-            const int64_t cap4 = (max_slots + 3) / 4 * 4;
-            const int64_t stride = (maxrow + 1 + 3) / 4 * 4;
+            const int64_t cap4 = std::max<int64_t>((max_slots + 3) / 4 * 4, kPBlock);   // >= kPBlock: prod[0 + tid] is always addressable
+            const int64_t stride = (maxrow + 8 + 3) / 4 * 4;   // + 8: k_lanczos_vec reads the diagonal starts eight at a time
             if (single && c->slots_cache_cols && (size_t)cap4 * 12 + (size_t)stride * 4 <= (size_t)224 * 1024 && !getenv("MACB_NO_JDS") &&
                 !c->h_col.empty()) {
                 const int ncta = c->p_ncta;
@@ -536,7 +536,7 @@ void setup_persist(macb_ctx* c) {
                     int* jdb = jd.data() + (size_t)b * stride;
                     int acc = 0;
                     for (int d = 0; d < stride; ++d) {
-                        jdb[d] = acc;
+                        jdb[d] = (d < (int)cnt.size() && (cnt[d] > 0 || d == 0)) ? acc : 0;   // padding entries point at slot 0 (never summed)
                         acc += cnt[d];
                     }
                     for (int t = 0; t < R; ++t) {

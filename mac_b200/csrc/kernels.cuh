@@ -1438,18 +1438,24 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
         if (warp < rows_warps) {
             double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
             if (has_row) {
+                // eight diagonals per trip, predicated instead of a scalar tail (jd is padded by 8 entries): the row sums
+                // are latency-bound (dependent shared-memory loads), not bandwidth-bound
                 const double* __restrict__ pt = prod + tid;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int d = 0;
-                for (; d + 4 <= len; d += 4) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+                for (int d = 0; d < len; d += 8) {
                     const int4 o = *reinterpret_cast<const int4*>(sjd + d);
+                    const int4 p = *reinterpret_cast<const int4*>(sjd + d + 4);
+                    const int r = len - d;
                     a0 += pt[o.x];
-                    a1 += pt[o.y];
-                    a2 += pt[o.z];
-                    a3 += pt[o.w];
+                    a1 += (r > 1) ? pt[o.y] : 0.0;
+                    a2 += (r > 2) ? pt[o.z] : 0.0;
+                    a3 += (r > 3) ? pt[o.w] : 0.0;
+                    a4 += (r > 4) ? pt[p.x] : 0.0;
+                    a5 += (r > 5) ? pt[p.y] : 0.0;
+                    a6 += (r > 6) ? pt[p.z] : 0.0;
+                    a7 += (r > 7) ? pt[p.w] : 0.0;
                 }
-                for (; d < len; ++d) a0 += pt[sjd[d]];
-                zr = fma(od, su, -((a0 + a1) + (a2 + a3)));   // (L u_phase)[row]
+                zr = fma(od, su, -(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))));   // (L u_phase)[row]
                 p1 = su * zr;
                 p2 = zr;
                 p3 = su * su;
