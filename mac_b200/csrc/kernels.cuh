@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
                 const double un = t + k4;                                    // u_phase[row]
                 const double zn = fma(d, t, -acc0);                         // (L u_phase)[row]; L 1 = 0 cancels k4
                 st_sector(D + 4 * (size_t)row, zn, un, u, d);
-                bj[row] = un;
+                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = fma(un, zn, p1);
                 p2 += zn;
                 p3 = fma(un, un, p3);
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
                 const double un = t + k4;
                 const double zn = fma(od, t, -(acc0 + acc1));
                 st_sector(D + 4 * (size_t)row, zn, un, ou, od);
-                bj[row] = un;
+                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = fma(un, zn, p1);
                 p2 += zn;
                 p3 = fma(un, un, p3);
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
                 const double un = t + k4;                       // u_phase[row]
                 const double zn = fma(od, t, -(acc0 + acc1));   // (L u_phase)[row]; L 1 = 0 cancels k4
                 st_sector(D + 4 * (size_t)row, zn, un, ou, od);
-                bj[row] = un;
+                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = fma(un, zn, p1);
                 p2 += zn;
                 p3 = fma(un, un, p3);
@@ -1171,7 +1171,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJ
                 const double un = t + k4;                  // u_phase[row]
                 const double zn = fma(od, t, -acc);        // (L u_phase)[row]; L 1 = 0 cancels k4
                 st_sector(D + 4 * (size_t)row, zn, un, ou, od);
-                bj[row] = un;
+                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = un * zn;
                 p2 = zn;
                 p3 = un * un;
@@ -1338,6 +1338,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
     __shared__ int stop_sm;
     __shared__ int stop_in;
     __shared__ int give_up;
+#ifdef MACB_PTIMING
+    __shared__ int dbg_retries;
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
     int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
     int* __restrict__ sjd = scol + J.prod_cap;
@@ -1352,6 +1355,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
         scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
     for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
     if (tid == 0) give_up = 0;
+#ifdef MACB_PTIMING
+    if (tid == 0) dbg_retries = 0;
+#endif
 
     int phase = a.st->phase;
     int cur = a.st->cur;
@@ -1402,6 +1408,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
                 if (c[q] >= 0) {
                     const double w = wq[q];
                     if (v[q] != v[q]) {   // producer has not written yet: gather again (bounded: never hang the device)
+#ifdef MACB_PTIMING
+                        atomicAdd(&dbg_retries, 1);
+#endif
                         unsigned int tries = 0;
                         do {
                             v[q] = ld_f64_if(U + (c[q] & CM), true);
@@ -1548,7 +1557,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
                        cf.k1, cf.k2, cf.k3, cf.k4, P1, P2, P3, P4);
 #endif
             __stcg(Un + row, un);
-            a.basis[(size_t)(phase + 1) * a.ld + row] = un;
+            __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
             __stcg(const_cast<double*>(U) + row, nanv);   // poison: this buffer is the target of phase + 1's pass B
             sq = su;
             su = un;
@@ -1567,7 +1576,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
             long long* e = a.timing + (size_t)64 * a.ncta * 5 + ((size_t)it * a.ncta + blockIdx.x) * 4;
             e[0] = tb0; e[1] = tb1; e[2] = tb2; e[3] = tb3;
             long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
-            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = t_coef;
+            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = (long long)atomicExch(&dbg_retries, 0);
             a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
         }
 #endif
@@ -1689,7 +1698,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, c
                 sec[3 * row] = zn;
                 sec[3 * row + 1] = un;
                 sec[3 * row + 2] = u;
-                bj[row] = un;
+                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = fma(un, zn, p1);
                 p2 += zn;
                 p3 = fma(un, un, p3);

@@ -36,6 +36,7 @@ if p1[2:33].any():
     print("slots kernel: pass 1 (gathers) mean %.0f max %.0f | pass 2 + block reduce mean %.0f" % (g.mean(), g.max(axis=1).mean(), (rows - g).mean()))
 if os.environ.get("PT_DETAIL"):
     t0 = t[:, :, 0]; tc = t[:, :, 3]
+    print("vec: slots that had to be gathered again per CTA and step (t[3] in the vec kernel): mean %.0f max %.0f" % (tc.mean(), tc.max(axis=1).mean()))
     print("jds: start->coef ready mean %.0f max %.0f min %.0f" % ((tc - t0).mean(), (tc - t0).max(axis=1).mean(), (tc - t0).min(axis=1).mean()))
     rr = rows.mean(axis=0); order = np.argsort(rr)
     print("rows per CTA: slowest", [(int(b), int(rr[b])) for b in order[-6:]], "fastest", [(int(b), int(rr[b])) for b in order[:4]])
