@@ -255,6 +255,7 @@ void build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, 
 void free_all(macb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->d_jval) cudaCtxResetPersistingL2Cache();   // the weights were pinned in the persisting part of L2 (setup_persist)
     if (c->lz_graph) cudaGraphExecDestroy(c->lz_graph);
     if (c->sel_graph) cudaGraphExecDestroy(c->sel_graph);
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
@@ -624,6 +625,25 @@ void setup_persist(macb_ctx* c) {
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 c->jds_vec = !getenv("MACB_NO_VEC");
                 c->persist_v = 5;
+                if (!getenv("MACB_NO_L2PIN")) {
+                    // keep the weights the Lanczos kernel streams every step (8 bytes per slot) in the persisting part of L2
+                    cudaDeviceProp prop;
+                    CK(cudaGetDeviceProperties(&prop, c->device));
+                    const size_t bytes = std::min<size_t>((size_t)c->nnz * sizeof(double), (size_t)prop.accessPolicyMaxWindowSize);
+                    const size_t carve = std::min<size_t>(bytes + (bytes >> 2), (size_t)prop.persistingL2CacheMaxSize);
+                    if (bytes > 0 && carve >= bytes && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                        cudaStreamAttrValue attr;
+                        memset(&attr, 0, sizeof(attr));
+                        attr.accessPolicyWindow.base_ptr = c->d_jval;
+                        attr.accessPolicyWindow.num_bytes = bytes;
+                        attr.accessPolicyWindow.hitRatio = 1.0f;
+                        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+                    } else {
+                        cudaGetLastError();
+                    }
+                }
                 if (c->have_x) {   // L(x) was assembled before the engine existed: fill the jagged copy of the weights once
                     k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
                     CK(cudaGetLastError());
