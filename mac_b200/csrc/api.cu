@@ -463,7 +463,11 @@ void setup_persist(macb_ctx* c) {
             c->persist_v = 1;   // a single row does not fit the staging buffer: use the row-parallel kernel
         } else {
             const int64_t total = (int64_t)c->nnz + 4 * (int64_t)n;
-            c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>((total + 4 * kPBlock - 1) / (4 * kPBlock), c->sm_count));
+            // work quantum per CTA: the all-to-all record exchange costs about the same for 20 or 148 CTAs, so small
+            // graphs are spread over many SMs (the counter barrier of the older engines preferred few)
+            int64_t quantum = 4 * kPBlock;
+            if (const char* env = getenv("MACB_CTA_QUANTUM")) quantum = std::max(64, atoi(env));
+            c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>((total + quantum - 1) / quantum, c->sm_count));
             rs.assign((size_t)c->p_ncta + 1, n);
             rs[0] = 0;
             int row = 0;
@@ -675,7 +679,7 @@ void setup_persist(macb_ctx* c) {
             rs[b] = row;
         }
     }
-    c->check_div = (c->p_ncta >= c->sm_count) ? 48 : 8;
+    c->check_div = (c->nnz >= 1000000) ? 48 : 8;   // steps of >= 10 us leave the host time for frequent checks
     if (const char* env = getenv("MACB_CHECK_DIV")) c->check_div = std::max(1, atoi(env));
     c->d_row_start = dalloc<int>(c->p_ncta + 1);
     CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
