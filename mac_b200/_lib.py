@@ -79,6 +79,7 @@ def lib():
     _sig(L.macb_spmv_engine, [H, C.c_int])
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
+    _sig(L.macb_host_build_jds, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int32, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip])
     _sig(L.macb_version, [], C.c_char_p)
     _lib = L
     return L
@@ -313,3 +314,23 @@ def host_build_pattern(n, fi, fj, ci, cj):
     if rc != MACB_OK:
         raise MacbError(f"macb_host_build_pattern failed ({rc}): {L.macb_last_error(None).decode()}")
     return rp, col[:nnz.value], eid[:nnz.value]
+
+
+def host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots=True, bankfit=True):
+    """Host helper (no GPU): the jagged-diagonal layout of k_lanczos_vec / k_lanczos_jds for a given CTA partition
+    `row_start` (len ncta + 1).  Returns (jrow, jlen, jcol, jeid, jd[ncta, stride])."""
+    L = lib()
+    rp, col, eid, row_start = _i32(rp), _i32(col), _i32(eid), _i32(row_start)
+    ncta = len(row_start) - 1
+    nnz = len(col)
+    jrow = np.empty(max(n, 1), dtype=np.int32)
+    jlen = np.empty(max(n, 1), dtype=np.int32)
+    jcol = np.empty(max(nnz, 1), dtype=np.int32)
+    jeid = np.empty(max(nnz, 1), dtype=np.int32)
+    jd = np.zeros(max(ncta * stride, 1), dtype=np.int32)
+    rc = L.macb_host_build_jds(n, _p(rp, _ip), _p(col, _ip), _p(eid, _ip), ncta, _p(row_start, _ip), int(stride),
+                               int(bool(sorted_slots)), int(bool(bankfit)), _p(jrow, _ip), _p(jlen, _ip), _p(jcol, _ip),
+                               _p(jeid, _ip), _p(jd, _ip))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_host_build_jds failed ({rc})")
+    return jrow[:n], jlen[:n], jcol[:nnz], jeid[:nnz], jd.reshape(ncta, stride) if ncta * stride else jd

@@ -439,6 +439,97 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     }
 }
 
+// Jagged-diagonal layout of the Lanczos kernels k_lanczos_jds / k_lanczos_vec (pure host code, also exported as
+// macb_host_build_jds for the CPU test-suite).  CTA b owns the rows row_start[b] .. row_start[b+1] and their slots
+// rp[row_start[b]] .. rp[row_start[b+1]].  Inside a CTA the rows are renumbered by decreasing length ("engine numbering",
+// jrow[engine row] = caller row, jlen = its length) so that diagonal d -- the d-th slot of every row that has one -- is the
+// contiguous range jd[b*stride + d] + t, t = engine row - row_start[b].  jcol holds ENGINE column ids.
+//   sorted = false: slot p of the CTA's range IS position p (jcol[p] = column of the product stored at p);
+//   sorted = true : the CTA's slots are stored in column order and carry their position: jcol = column | position << 17
+//                   (needs n <= 2^17 and <= 2^14 slots per CTA); which diagonal of its row a slot uses is free, and with
+//                   bankfit it is chosen so that the 16 positions of a half-warp fall into different 8-byte banks.
+void build_jds_layout(int n, const int32_t* rp, const int32_t* col, const int32_t* eid, int ncta, const int* row_start, int stride,
+                      bool sorted, bool bankfit, int* jrow, int* jlen, int* jcol, int* jeid, int* jd) {
+    std::vector<int> order, cnt, inv((size_t)n);   // inv[caller id] = engine id
+    for (int b = 0; b < ncta; ++b) {
+        const int ra = row_start[b], R = row_start[b + 1] - ra;
+        order.resize(R);
+        for (int t = 0; t < R; ++t) order[t] = ra + t;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
+        for (int t = 0; t < R; ++t) {
+            jrow[ra + t] = order[t];
+            inv[order[t]] = ra + t;
+        }
+    }
+    std::vector<std::pair<int, int>> key;
+    std::vector<int> tc, te, pos_row, newpos;
+    std::vector<std::vector<unsigned char>> used_d;
+    for (int b = 0; b < ncta; ++b) {
+        const int ra = row_start[b], rb = row_start[b + 1], R = rb - ra;
+        const int sa = rp[ra], ns = rp[rb] - sa;
+        cnt.assign((size_t)stride, 0);   // cnt[d] = rows with more than d slots
+        for (int t = 0; t < R; ++t) {
+            const int row = jrow[ra + t], len = rp[row + 1] - rp[row];
+            jlen[ra + t] = len;
+            for (int d = 0; d < len; ++d) cnt[d]++;
+        }
+        int* jdb = jd + (size_t)b * stride;
+        int acc = 0;
+        for (int d = 0; d < stride; ++d) {
+            jdb[d] = (cnt[d] > 0 || d == 0) ? acc : 0;   // padding entries point at slot 0 (never summed)
+            acc += cnt[d];
+        }
+        for (int t = 0; t < R; ++t) {
+            const int row = jrow[ra + t], s0 = rp[row], len = rp[row + 1] - s0;
+            for (int d = 0; d < len; ++d) {
+                jcol[(size_t)sa + jdb[d] + t] = inv[col[(size_t)s0 + d]];
+                jeid[(size_t)sa + jdb[d] + t] = eid[(size_t)s0 + d];
+            }
+        }
+        if (!sorted) continue;
+        key.resize(ns);
+        for (int q = 0; q < ns; ++q) key[q] = {jcol[(size_t)sa + q], q};
+        std::sort(key.begin(), key.end());
+        tc.resize(ns);
+        te.resize(ns);
+        pos_row.resize(ns);
+        newpos.resize(ns);
+        used_d.resize((size_t)R);
+        for (int t = 0; t < R; ++t) {
+            const int len = jlen[ra + t];
+            used_d[t].assign((size_t)len, 0);
+            for (int d = 0; d < len; ++d) pos_row[(size_t)jdb[d] + t] = t;
+        }
+        for (int g0 = 0; g0 < ns; g0 += 16) {
+            unsigned int banks = 0;
+            for (int q = g0; q < std::min(ns, g0 + 16); ++q) {
+                const int t = pos_row[key[q].second];
+                std::vector<unsigned char>& u = used_d[t];
+                int pick = -1, fallback = -1;
+                for (int d = 0; d < (int)u.size(); ++d) {
+                    if (u[d]) continue;
+                    if (fallback < 0) fallback = d;
+                    if (!bankfit) break;
+                    if (!((banks >> ((jdb[d] + t) & 15)) & 1u)) {
+                        pick = d;
+                        break;
+                    }
+                }
+                if (pick < 0) pick = fallback;
+                u[pick] = 1;
+                banks |= 1u << ((jdb[pick] + t) & 15);
+                newpos[q] = jdb[pick] + t;
+            }
+        }
+        for (int q = 0; q < ns; ++q) {
+            tc[q] = key[q].first | (newpos[q] << 17);
+            te[q] = jeid[(size_t)sa + key[q].second];
+        }
+        std::copy(tc.begin(), tc.end(), jcol + sa);
+        std::copy(te.begin(), te.end(), jeid + sa);
+    }
+}
+
 void setup_persist(macb_ctx* c) {
     const int n = c->n, W = c->W;
     std::vector<int> rs;
@@ -516,97 +607,10 @@ void setup_persist(macb_ctx* c) {
                 const int ncta = c->p_ncta;
                 std::vector<int> jrow((size_t)n), jlen((size_t)n), jcol((size_t)c->nnz), jeid((size_t)c->nnz),
                     jd((size_t)ncta * stride, 0);
-                std::vector<int> order, cnt, inv((size_t)n);   // inv[caller id] = engine id
-                for (int b = 0; b < ncta; ++b) {
-                    const int ra = rs[b], R = rs[b + 1] - ra;
-                    order.resize(R);
-                    for (int t = 0; t < R; ++t) order[t] = ra + t;
-                    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-                        return c->h_rp[x + 1] - c->h_rp[x] > c->h_rp[y + 1] - c->h_rp[y];
-                    });
-                    for (int t = 0; t < R; ++t) {
-                        jrow[ra + t] = order[t];
-                        inv[order[t]] = ra + t;
-                    }
-                }
-                for (int b = 0; b < ncta; ++b) {
-                    const int ra = rs[b], rb = rs[b + 1], R = rb - ra;
-                    const int sa = c->h_rp[ra];
-                    cnt.assign((size_t)stride, 0);   // cnt[d] = rows with more than d slots
-                    for (int t = 0; t < R; ++t) {
-                        const int row = jrow[ra + t], len = c->h_rp[row + 1] - c->h_rp[row];
-                        jlen[ra + t] = len;
-                        for (int d = 0; d < len; ++d) cnt[d]++;
-                    }
-                    int* jdb = jd.data() + (size_t)b * stride;
-                    int acc = 0;
-                    for (int d = 0; d < stride; ++d) {
-                        jdb[d] = (d < (int)cnt.size() && (cnt[d] > 0 || d == 0)) ? acc : 0;   // padding entries point at slot 0 (never summed)
-                        acc += cnt[d];
-                    }
-                    for (int t = 0; t < R; ++t) {
-                        const int row = jrow[ra + t], s0 = c->h_rp[row], len = c->h_rp[row + 1] - s0;
-                        for (int d = 0; d < len; ++d) {
-                            jcol[(size_t)sa + jdb[d] + t] = inv[c->h_col[(size_t)s0 + d]];
-                            jeid[(size_t)sa + jdb[d] + t] = c->h_eid[(size_t)s0 + d];
-                        }
-                    }
-                }
                 // optional: store every CTA's slots in column order (positions of the products packed beside the column)
                 c->jds_sorted = !(getenv("MACB_JDS_SORT") && atoi(getenv("MACB_JDS_SORT")) == 0) && n <= (1 << 17) && cap4 <= (1 << 14);
-                if (c->jds_sorted) {
-                    std::vector<std::pair<int, int>> key;
-                    std::vector<int> tc, te;
-                    for (int b = 0; b < ncta; ++b) {
-                        const int sa = c->h_rp[rs[b]], ns = c->h_rp[rs[b + 1]] - sa;
-                        key.resize(ns);
-                        for (int q = 0; q < ns; ++q) key[q] = {jcol[(size_t)sa + q], q};
-                        std::sort(key.begin(), key.end());
-                        tc.resize(ns);
-                        te.resize(ns);
-                        // Which diagonal a slot's product goes to is free within its row (pass 2 sums all of them).  A
-                        // half-warp stores 16 products of 8 bytes: conflict-free iff their positions differ mod 16.  Walk
-                        // the column-sorted slots in groups of 16 and give every slot a still unused diagonal of its row
-                        // whose position falls into a bank the group has not used yet (first fit; any free one otherwise).
-                        const int R = rs[b + 1] - rs[b];
-                        const int* jdb = jd.data() + (size_t)b * stride;
-                        std::vector<int> pos_row((size_t)ns), newpos((size_t)ns);
-                        std::vector<std::vector<unsigned char>> used_d((size_t)R);
-                        for (int t = 0; t < R; ++t) {
-                            const int len = jlen[rs[b] + t];
-                            used_d[t].assign((size_t)len, 0);
-                            for (int d = 0; d < len; ++d) pos_row[(size_t)jdb[d] + t] = t;
-                        }
-                        const bool avoid = !getenv("MACB_NO_BANKFIT");
-                        for (int g0 = 0; g0 < ns; g0 += 16) {
-                            unsigned int banks = 0;
-                            for (int q = g0; q < std::min(ns, g0 + 16); ++q) {
-                                const int t = pos_row[key[q].second];
-                                std::vector<unsigned char>& u = used_d[t];
-                                int pick = -1, fallback = -1;
-                                for (int d = 0; d < (int)u.size(); ++d) {
-                                    if (u[d]) continue;
-                                    if (fallback < 0) fallback = d;
-                                    if (!avoid) break;
-                                    if (!((banks >> ((jdb[d] + t) & 15)) & 1u)) {
-                                        pick = d;
-                                        break;
-                                    }
-                                }
-                                if (pick < 0) pick = fallback;
-                                u[pick] = 1;
-                                banks |= 1u << ((jdb[pick] + t) & 15);
-                                newpos[q] = jdb[pick] + t;
-                            }
-                        }
-                        for (int q = 0; q < ns; ++q) {
-                            tc[q] = key[q].first | (newpos[q] << 17);
-                            te[q] = jeid[(size_t)sa + key[q].second];
-                        }
-                        std::copy(tc.begin(), tc.end(), jcol.begin() + sa);
-                        std::copy(te.begin(), te.end(), jeid.begin() + sa);
-                    }
-                }
+                build_jds_layout(n, c->h_rp.data(), c->h_col.data(), c->h_eid.data(), ncta, rs.data(), (int)stride, c->jds_sorted,
+                                 !getenv("MACB_NO_BANKFIT"), jrow.data(), jlen.data(), jcol.data(), jeid.data(), jd.data());
                 c->d_jrow = dalloc<int>(n);
                 c->d_jlen = dalloc<int>(n);
                 c->d_jcol = dalloc<int>(c->nnz);
@@ -1185,6 +1189,25 @@ int macb_host_build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int3
         g_create_error = e.msg;
         return e.code;
     }
+}
+
+int macb_host_build_jds(int32_t n, const int32_t* rp, const int32_t* col, const int32_t* eid, int32_t ncta, const int32_t* row_start,
+                        int32_t stride, int sorted, int bankfit, int32_t* jrow, int32_t* jlen, int32_t* jcol, int32_t* jeid, int32_t* jd) {
+    if (n < 0 || ncta < 1 || !rp || !row_start || !jrow || !jlen || !jcol || !jeid || !jd) return MACB_ERR_ARG;
+    if (sorted && n > (1 << 17)) return MACB_ERR_ARG;
+    for (int b = 0; b < ncta; ++b) {
+        const int R = row_start[b + 1] - row_start[b];
+        const int64_t ns = (int64_t)rp[row_start[b + 1]] - rp[row_start[b]];
+        if (R < 0 || (sorted && ns > (1 << 14))) return MACB_ERR_ARG;
+        for (int r = row_start[b]; r < row_start[b + 1]; ++r)
+            if (rp[r + 1] - rp[r] + 1 > stride) return MACB_ERR_ARG;
+    }
+    try {
+        build_jds_layout(n, rp, col, eid, ncta, row_start, stride, sorted != 0, bankfit != 0, jrow, jlen, jcol, jeid, jd);
+    } catch (const std::bad_alloc&) {
+        return MACB_ERR_NOMEM;
+    }
+    return MACB_OK;
 }
 
 int macb_tridiag_smallest(const double* a, const double* b, int k, double* theta, double* s) {

@@ -188,3 +188,65 @@ def test_synthetic_generators_are_deterministic():
     assert (np.abs(ci - cj) > 1).all() and len(set(zip(ci.tolist(), cj.tolist()))) == 5000
     fixed, cand, n, k, x0 = synth.headline(n=2000, m=20000)
     assert k == 4000 and x0.sum() == 4000 and len(fixed[0]) == n - 1
+
+
+@pytest.mark.parametrize("sorted_slots,bankfit", [(False, False), (True, False), (True, True)])
+def test_jagged_diagonal_layout_invariants(sorted_slots, bankfit):
+    """The layout k_lanczos_vec / k_lanczos_jds read (csrc/api.cu build_jds_layout), checked on the host: engine
+    numbering is a within-CTA permutation by decreasing length, every row owns exactly one position per diagonal
+    jd[d] + t, positions tile the CTA's slot range, and every slot still carries its (row, column, edge) triple."""
+    from mac_b200 import _lib
+    fixed, cand, n = synth.chain_plus_random(700, 5000, seed=11, weighted=True)
+    rp, col, eid = _lib.host_build_pattern(n, fixed[0], fixed[1], cand[0], cand[1])
+    row_start = np.array([0, 150, 151, 400, 700], dtype=np.int32)      # four CTAs, one with a single row
+    lens = np.diff(rp)
+    stride = ((lens.max() + 8 + 3) // 4) * 4
+    jrow, jlen, jcol, jeid, jd = _lib.host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots, bankfit)
+    assert sorted(jrow.tolist()) == list(range(n))
+    inv = np.empty(n, dtype=np.int64)
+    inv[jrow] = np.arange(n)
+    conflicts = groups = 0
+    for b in range(len(row_start) - 1):
+        ra, rb = row_start[b], row_start[b + 1]
+        sa, ns = rp[ra], rp[rb] - rp[ra]
+        assert sorted(jrow[ra:rb].tolist()) == list(range(ra, rb))           # permutation inside the CTA
+        assert np.array_equal(jlen[ra:rb], lens[jrow[ra:rb]])
+        assert np.all(np.diff(jlen[ra:rb]) <= 0)                              # decreasing length
+        cnt = np.array([(jlen[ra:rb] > d).sum() for d in range(stride)])
+        assert np.array_equal(jd[b][cnt > 0], np.concatenate([[0], np.cumsum(cnt)[:-1]])[cnt > 0])
+        words = jcol[sa:sa + ns]
+        if sorted_slots:
+            cols, pos = words & 0x1ffff, (words >> 17) & 0x3fff
+            assert np.all(np.diff(cols) >= 0)                                 # column order
+            for g0 in range(0, ns, 16):
+                grp = pos[g0:g0 + 16] & 15
+                groups += 1
+                conflicts += len(grp) - len(set(grp.tolist()))
+        else:
+            cols, pos = words, np.arange(ns)
+        assert sorted(pos.tolist()) == list(range(ns))                        # positions tile the slot range
+        # position -> (engine row t, diagonal d): the d with jd[d] <= pos < jd[d] + cnt[d]
+        starts = jd[b][:int((cnt > 0).sum())]
+        d_of = np.searchsorted(starts, pos, side="right") - 1
+        t_of = pos - starts[d_of]
+        assert np.all(t_of < cnt[d_of])
+        rows = jrow[ra + t_of]                                                # caller row of every slot
+        triples = sorted(zip(rows.tolist(), jrow[cols].tolist(), jeid[sa:sa + ns].tolist()))
+        ref = sorted((r, int(col[s]), int(eid[s])) for r in range(ra, rb) for s in range(rp[r], rp[r + 1]))
+        assert triples == ref
+        # every row uses each of its diagonals exactly once
+        per_row = {}
+        for t, d in zip(t_of.tolist(), d_of.tolist()):
+            per_row.setdefault(t, []).append(d)
+        assert all(sorted(ds) == list(range(jlen[ra + t])) for t, ds in per_row.items())
+    if sorted_slots and bankfit:
+        # first fit removes most of the bank collisions a position-by-CSR-order placement has (5.6 -> 1.4 per group here)
+        _, _, jcol0, _, _ = _lib.host_build_jds(n, rp, col, eid, row_start, stride, True, False)
+        base = 0
+        for b in range(len(row_start) - 1):
+            sa, ns = rp[row_start[b]], rp[row_start[b + 1]] - rp[row_start[b]]
+            pos0 = (jcol0[sa:sa + ns] >> 17) & 0x3fff
+            for g0 in range(0, ns, 16):
+                grp = pos0[g0:g0 + 16] & 15
+                base += len(grp) - len(set(grp.tolist()))
+        assert conflicts < 0.4 * base
