@@ -90,6 +90,7 @@ struct macb_ctx {
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool jds_sorted = false;
+    bool small_v2 = true;          // k_lanczos_small2 (3 CTA barriers per step) instead of k_lanczos_small (6)
     // chunked jagged-diagonal SpMV (k_spmv_jds): built on demand by macb_spmv_engine(h, 1)
     int spmv_engine = 0;           // 0: k_spmv (CSR, W lanes per row), 1: k_spmv_jds
     int sj_nchunks = 0;
@@ -415,7 +416,8 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.stop = async ? c->h_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
     if (c->persist_v == 4) {
-        k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        if (c->small_v2) k_lanczos_small2<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        else k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
         CK(cudaGetLastError());
     } else if (c->persist_v == 5) {
         LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
@@ -541,6 +543,8 @@ void setup_persist(macb_ctx* c) {
         c->p_ncta = 1;
         c->slots_smem = small_bytes;
         CK(cudaFuncSetAttribute((const void*)k_lanczos_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+        CK(cudaFuncSetAttribute((const void*)k_lanczos_small2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+        c->small_v2 = !getenv("MACB_SMALL_V1");
         rs.assign(2, n);
         rs[0] = 0;
     }
@@ -1688,7 +1692,7 @@ const char* macb_lanczos_kernel_name(macb_handle h) {
     if (!h->persist) return "k_spmv+k_lanczos_b";
     switch (h->persist_v) {
         case 5: return h->jds_vec ? "k_lanczos_vec" : "k_lanczos_jds";
-        case 4: return "k_lanczos_small";
+        case 4: return h->small_v2 ? "k_lanczos_small2" : "k_lanczos_small";
         case 3: return "k_lanczos_slots";
         default: return "k_lanczos_persist";
     }

@@ -1767,6 +1767,149 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, c
     }
 }
 
+// ---- K3, single-CTA form, second generation (default for small graphs) ------------------------------------------
+// Same problem class as k_lanczos_small, organised like k_lanczos_vec: the current Lanczos vector is materialised in
+// shared memory, every thread keeps (u_j, u_{j-1}) of its rows in registers, the block-wide sums are finished by EVERY
+// warp redundantly (one shared-memory round instead of a second stage + barrier), the coefficient chain runs on all
+// threads.  Three CTA barriers per step instead of six.  State hand-over through the sector buffer is compatible with
+// k_lz_persist_init and with itself: (0, u_j, u_{j-1}, diag) with coefficients (0, 1, 0, 0).
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, const double* __restrict__ diag) {
+    extern __shared__ double smem_small[];
+    const int n = a.n;
+    const int nnz = a.rp[n];
+    double* __restrict__ uvec = smem_small;            // [n]   u_phase
+    double* __restrict__ prod = uvec + n;              // [nnz]
+    double* __restrict__ wts = prod + nnz;             // [nnz]
+    __shared__ double sm[4 * kPWarps];
+    __shared__ int stop_small;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) stop_small = 0;
+
+    int pc[kSmallSlots];
+#pragma unroll
+    for (int j = 0; j < kSmallSlots; ++j) {
+        const int i = tid + kPBlock * j;
+        pc[j] = (i < nnz) ? a.col[i] : 0;
+        if (i < nnz) wts[i] = a.val[i];
+    }
+    int rs0[kSmallRows], rs1[kSmallRows];
+    double rd[kSmallRows], su[kSmallRows], sq[kSmallRows];
+    int phase = a.st->phase;
+    double* __restrict__ G = a.sect[0];
+    {
+        const double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
+#pragma unroll
+        for (int r = 0; r < kSmallRows; ++r) {
+            const int row = tid + kPBlock * r;
+            rs0[r] = (row < n) ? a.rp[row] : 0;
+            rs1[r] = (row < n) ? a.rp[row + 1] : 0;
+            rd[r] = (row < n) ? diag[row] : 0.0;
+            su[r] = 0.0;
+            sq[r] = 0.0;
+            if (row < n) {
+                double z, u, q, d;
+                ld_sector(G + 4 * (size_t)row, z, u, q, d);
+                su[r] = fma(k1, z, fma(k2, u, k3 * q)) + k4;   // u_phase (a sector engine may have left z != 0)
+                sq[r] = u;
+                if (k1 == 0.0 && k2 == 1.0 && k3 == 0.0) sq[r] = q;   // own hand-over format: (0, u_j, u_{j-1}, diag)
+                uvec[row] = su[r];
+                if (phase == 0) a.basis[row] = su[r];
+            }
+        }
+    }
+    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed step
+    const double inv_n = 1.0 / (double)a.n;
+    int stop_probe = 0;
+    bool stop_all = false;
+    __syncthreads();
+
+    for (int it = 0; it < a.nphases && !stop_all; ++it) {
+        // host stop flag: requested every 8th phase, looked at 7 phases later (a host-memory load takes microseconds)
+        if (tid == 0 && a.stop && (it & 7) == 0)
+            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_probe) : "l"(a.stop));
+        // ---- pass 1: products from the shared-memory vector
+#pragma unroll
+        for (int j = 0; j < kSmallSlots; ++j) {
+            const int i = tid + kPBlock * j;
+            if (i < nnz) {
+                const double w = wts[i];
+                prod[i] = (w != 0.0) ? w * uvec[pc[j]] : 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: z for the thread's rows, partial sums
+        double zr[kSmallRows];
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kSmallRows; ++r) {
+            const int row = tid + kPBlock * r;
+            zr[r] = 0.0;
+            if (row < n) {
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = rs0[r];
+                for (; i + 1 < rs1[r]; i += 2) {
+                    acc0 += prod[i];
+                    acc1 += prod[i + 1];
+                }
+                if (i < rs1[r]) acc0 += prod[i];
+                zr[r] = fma(rd[r], su[r], -(acc0 + acc1));
+                p1 = fma(su[r], zr[r], p1);
+                p2 += zr[r];
+                p3 = fma(su[r], su[r], p3);
+                p4 += su[r];
+            }
+        }
+        {
+            const double rsum = warp_sum4(p1, p2, p3, p4, lane);
+            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = rsum;
+        }
+        if (tid == 0 && a.stop && (it & 7) == 7) stop_small = stop_probe;
+        __syncthreads();
+        // ---- every warp finishes the block sums itself, then the coefficient chain on every thread
+        const double t4 = warp_sum4(sm[lane], sm[kPWarps + lane], sm[2 * kPWarps + lane], sm[3 * kPWarps + lane], lane);
+        const double P1 = __shfl_sync(0xffffffffu, t4, 0), P2 = __shfl_sync(0xffffffffu, t4, 8),
+                     P3 = __shfl_sync(0xffffffffu, t4, 16), P4 = __shfl_sync(0xffffffffu, t4, 24);
+        const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
+        stop_all = (stop_small != 0);
+        // ---- pass B: u_{phase+1} for the thread's rows
+        double* __restrict__ bn = a.basis + (size_t)(phase + 1) * a.ld;
+#pragma unroll
+        for (int r = 0; r < kSmallRows; ++r) {
+            const int row = tid + kPBlock * r;
+            if (row < n) {
+                const double un = fma(cf.k1, zr[r], fma(cf.k2, su[r], cf.k3 * sq[r])) + cf.k4;
+                uvec[row] = un;
+                __stcs(bn + row, un);
+                sq[r] = su[r];
+                su[r] = un;
+            }
+        }
+        if (tid == 0) {
+            a.alpha[phase] = cf.alpha;
+            a.beta[phase] = cf.beta;
+            if (a.ab_host)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(cf.alpha), "d"(cf.beta) : "memory");
+        }
+        beta_prev = cf.binv;
+        usum_prev = P4;
+        ++phase;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < kSmallRows; ++r) {
+        const int row = tid + kPBlock * r;
+        if (row < n) st_sector(G + 4 * (size_t)row, 0.0, su[r], sq[r], rd[r]);
+    }
+    if (tid == 0) {
+        a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
+        a.st->cur = 0;
+        a.st->k1 = 0.0; a.st->k2 = 1.0; a.st->k3 = 0.0; a.st->k4 = 0.0;
+        a.st->beta_prev = beta_prev;
+        a.st->usum_prev = usum_prev;
+    }
+}
+
 // sectors for phase 0: (0, src_i, 0, diag_i) with (k1,k2,k3,k4) = (0,1,0,0)  =>  u_0 = src
 __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double* __restrict__ src,
                                                             const double* __restrict__ diag, double* __restrict__ sect0,
