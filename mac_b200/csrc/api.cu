@@ -804,6 +804,9 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
     int k_seen = 0;        // alpha/beta copied into h_alpha/h_beta for indices < k_seen
     double theta_prev = std::numeric_limits<double>::infinity(), theta_delta = -1.0;
     bool invariant = false;
+    static const bool adaptive_checks = !getenv("MACB_FIXED_CHECKS");
+    double est_prev = 0.0;
+    int k_prev = 0;
     while (true) {
         // ---- launch (or resume) the kernel for everything that is left of this cycle
         const int nph = (k_limit + 1) - phases_done;
@@ -906,7 +909,22 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 // estimate passed but the true residual did not: resume the kernel and look again a little later
                 k_next = next_check(need, c->check_div);
             } else {
-                k_next = next_check(need, c->check_div);
+                // Next check: the residual estimate of a resolved Ritz pair decays geometrically, so two consecutive
+                // estimates predict where it crosses the threshold; look again half-way there (Lanczos converges
+                // superlinearly, the prediction errs on the late side), never closer than 4 steps, never further than
+                // the fixed k/div schedule allows while the estimate is not yet decreasing.  The schedule depends on
+                // (alpha, beta) only -- not on timing -- so a solve stays a pure function of its input.
+                const double target = tol * lnorm / (0.88 * sqrtn);
+                int nk = next_check(need, c->check_div);
+                if (adaptive_checks && est_prev > 0.0 && est > target && est < est_prev && k > k_prev) {
+                    const double slope = (std::log(est) - std::log(est_prev)) / (double)(k - k_prev);
+                    const double pred = (std::log(target) - std::log(est)) / slope;   // steps still to go at this rate
+                    const double cap = std::max(16.0, 0.25 * (double)k);
+                    nk = need + (int)std::max(4.0, std::min(0.5 * pred, cap));
+                }
+                k_prev = k;
+                est_prev = est;
+                k_next = nk;
             }
         }
         (void)k_conv;
