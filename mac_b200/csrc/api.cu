@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <thread>
 
 #include "kernels.cuh"
 #include "tridiag.h"
@@ -805,6 +806,8 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
     double theta_prev = std::numeric_limits<double>::infinity(), theta_delta = -1.0;
     bool invariant = false;
     static const bool adaptive_checks = !getenv("MACB_FIXED_CHECKS");
+    double t_launch = 0.0;
+    int k_launch = 0;
     double est_prev = 0.0;
     int k_prev = 0;
     while (true) {
@@ -819,6 +822,8 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             c->ab_dirty = phases_done;
             *(volatile int*)c->h_stop = 0;
             launch_persist(c, nph, true);
+            t_launch = us();
+            k_launch = phases_done;
         }
         bool stopped = false;
         int k_conv = -1;
@@ -827,6 +832,17 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
             const int need = std::min(k_next, k_limit);
             bool kernel_done = false;
             const double tw0 = us();
+            // A far-away check point: sleep through half of the predicted wait instead of burning a core (several handles
+            // sweeping budgets concurrently share the host's cores with each other's Rayleigh-Ritz).  The step time is
+            // measured on this very launch; the stop decision does not depend on when the host looks.
+            if (k_seen > 32 && std::isnan(ab[2 * need + 1])) {
+                int latest = k_seen;
+                while (latest < need && !std::isnan(ab[2 * latest + 1])) ++latest;
+                const double us_per_step = (tw0 - t_launch) / (double)std::max(latest - k_launch, 1);
+                const double wait_us = 0.5 * us_per_step * (double)(need - latest);
+                if (latest > k_launch + 16 && wait_us > 1000.0)
+                    std::this_thread::sleep_for(std::chrono::microseconds((long long)std::min(wait_us, 20000.0)));
+            }
             // spin on the mapped memory; ask the driver whether the kernel has ended only now and then (the query
             // takes the driver lock: with several handles sweeping budgets concurrently that lock is the bottleneck)
             for (unsigned int spin = 1; std::isnan(ab[2 * need + 1]); ++spin) {
