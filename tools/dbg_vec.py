@@ -1,3 +1,5 @@
+"""Debug target for k_lanczos_vec: `make debugvec` builds mac_b200/libmacb200_debug.so with bounded spin loops that print which
+CTA / column / inbox slot they gave up on and every CTA's progress (MACB_LIB=mac_b200/libmacb200_debug.so python tools/dbg_vec.py)."""
 import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mac_b200 import synth
