@@ -101,6 +101,7 @@ struct macb_ctx {
     bool sj_col16 = false;
     int64_t* d_sj_chunk_slot = nullptr;
     double* d_sj_val = nullptr;
+    int vec_batch = 5;             // gathers in flight per thread in k_lanczos_vec (3..8, chosen from the slots per thread)
     bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
@@ -424,8 +425,17 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
                     c->d_diag, c->d_jrow};
         void* params[] = {&a, &J};
-        void* fn = c->jds_vec ? (c->jds_sorted ? (void*)k_lanczos_vec<true> : (void*)k_lanczos_vec<false>)
-                              : (c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>);
+        void* fn = c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>;
+        if (c->jds_vec) {
+            switch (c->vec_batch) {
+                case 3: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 3> : (void*)k_lanczos_vec<false, 3>; break;
+                case 4: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 4> : (void*)k_lanczos_vec<false, 4>; break;
+                case 6: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 6> : (void*)k_lanczos_vec<false, 6>; break;
+                case 7: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 7> : (void*)k_lanczos_vec<false, 7>; break;
+                case 8: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 8> : (void*)k_lanczos_vec<false, 8>; break;
+                default: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 5> : (void*)k_lanczos_vec<false, 5>; break;
+            }
+        }
         CK(cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
     } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
@@ -634,8 +644,27 @@ void setup_persist(macb_ctx* c) {
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
-                CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
-                CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+#define MACB_VEC_SMEM(VB_)                                                                                                                   \
+    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<false, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem)); \
+    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
+#undef MACB_VEC_SMEM
+                {   // gathers in flight per thread: the batch size whose last batch of a step is fullest (see kernels.cuh)
+                    const double pt = (double)max_slots / (double)kPBlock;
+                    double best = -1.0;
+                    for (int vb = 3; vb <= 8; ++vb) {
+                        const int nb = std::max(1, (int)std::ceil(pt / vb));
+                        const double fill = (pt - (double)(nb - 1) * vb) / vb;
+                        if (fill > best + 1e-9 || (std::fabs(fill - best) <= 1e-9 && vb > c->vec_batch)) {
+                            best = fill;
+                            c->vec_batch = vb;
+                        }
+                    }
+                    if (const char* env = getenv("MACB_VEC_BATCH")) {
+                        const int vb = atoi(env);
+                        if (vb >= 3 && vb <= 8) c->vec_batch = vb;
+                    }
+                }
                 c->jds_vec = !getenv("MACB_NO_VEC");
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {

@@ -1316,10 +1316,11 @@ __global__ void __launch_bounds__(kBlock) k_lz_vec_init(int n, const double* __r
     }
 }
 
-#ifndef MACB_VEC_BATCH
-#define MACB_VEC_BATCH 8
-#endif
-constexpr int kVecBatch = MACB_VEC_BATCH;   // gathers in flight per thread
+// Gathers in flight per thread (template parameter VB of k_lanczos_vec).  What matters is how full the LAST batch of a
+// step is: every batch costs a full memory round trip whether one slot or VB of them ride on it.  Measured at the
+// headline size (14.55 slots per thread), us per step: VB = 3: 9.77, 4: 10.15, 5: 9.75, 6: 10.75, 7: 11.12, 8: 10.67 (and
+// a few spills), 10: 11.7.  The host picks the VB in 3..8 whose last batch is fullest (one full batch when a thread has
+// at most 8 slots).
 #ifdef MACB_DEBUG_VEC
 __device__ int g_dbg_count = 0;
 __device__ int g_prog[256];
@@ -1328,8 +1329,9 @@ __device__ int g_prog[256];
 #define MACB_PROG(stage) do {} while (0)
 #endif
 
-template <bool SORTED>
+template <bool SORTED, int VB>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJdsArgs J) {
+    constexpr int kVecBatch = VB;
     constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
 #define MACB_DST(cc, jj) (SORTED ? (((cc) >> 17) & 0x3fff) : (jj))
     extern __shared__ double prod[];
