@@ -250,3 +250,50 @@ def test_jagged_diagonal_layout_invariants(sorted_slots, bankfit):
                 grp = pos0[g0:g0 + 16] & 15
                 base += len(grp) - len(set(grp.tolist()))
         assert conflicts < 0.4 * base
+
+
+def test_jagged_diagonal_layout_on_ragged_random_graphs():
+    """Same invariants on many small ragged inputs: isolated nodes (rows without slots), CTAs without rows, CTAs with a
+    single row, hubs, both slot orders.  Exercises the corner cases the GPU tests cannot enumerate."""
+    from mac_b200 import _lib
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        n = int(rng.integers(2, 70))
+        m = int(rng.integers(0, 4 * n))
+        # a partial chain (some nodes stay isolated), random candidates, one hub
+        keep = rng.random(n - 1) < 0.7
+        fi = np.arange(n - 1, dtype=np.int32)[keep]
+        fj = fi + 1
+        ci = rng.integers(0, n, size=m).astype(np.int32)
+        cj = rng.integers(0, n, size=m).astype(np.int32)
+        if n > 8:
+            hub = np.full(n // 2, 3, dtype=np.int32)
+            ci = np.concatenate([ci, hub]); cj = np.concatenate([cj, rng.integers(0, n, size=len(hub)).astype(np.int32)])
+        rp, col, eid = _lib.host_build_pattern(n, fi, fj, ci, cj)
+        lens = np.diff(rp)
+        stride = int(((lens.max(initial=0) + 8 + 3) // 4) * 4)
+        cuts = np.sort(rng.integers(0, n + 1, size=int(rng.integers(0, 5))))
+        row_start = np.concatenate([[0], cuts, [n]]).astype(np.int32)          # may contain empty CTAs
+        for sorted_slots in (False, True):
+            jrow, jlen, jcol, jeid, jd = _lib.host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots, True)
+            assert sorted(jrow.tolist()) == list(range(n))
+            for b in range(len(row_start) - 1):
+                ra, rb = int(row_start[b]), int(row_start[b + 1])
+                sa, ns = int(rp[ra]), int(rp[rb] - rp[ra])
+                assert sorted(jrow[ra:rb].tolist()) == list(range(ra, rb))
+                assert np.array_equal(jlen[ra:rb], lens[jrow[ra:rb]])
+                assert np.all(np.diff(jlen[ra:rb]) <= 0)
+                if ns == 0:
+                    continue
+                words = jcol[sa:sa + ns]
+                cols, pos = ((words & 0x1ffff, (words >> 17) & 0x3fff) if sorted_slots else (words, np.arange(ns)))
+                assert sorted(pos.tolist()) == list(range(ns))
+                cnt = np.array([(jlen[ra:rb] > d).sum() for d in range(stride)])
+                starts = jd[b][:int((cnt > 0).sum())]
+                d_of = np.searchsorted(starts, pos, side="right") - 1
+                t_of = pos - starts[d_of]
+                assert np.all(t_of < cnt[d_of])
+                rows = jrow[ra + t_of]
+                triples = sorted(zip(rows.tolist(), jrow[cols].tolist(), jeid[sa:sa + ns].tolist()))
+                ref = sorted((r, int(col[s_]), int(eid[s_])) for r in range(ra, rb) for s_ in range(rp[r], rp[r + 1]))
+                assert triples == ref, (trial, b, sorted_slots)
