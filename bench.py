@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 METRIC = "fw_iters_per_sec"
 UNIT = "it/s"
 N_NODES, N_CAND, BUDGET_FRAC = 100_000, 1_000_000, 0.2
+PARITY_TOL = 1e-6   # north-star: Fiedler value within 1e-6 relative of the reference CPU path
 WORKLOAD = "chain+random graph n=100000, 1000000 candidate edges, K=200000, x_init=first-K (BASELINE configs[4])"
 
 
@@ -111,16 +112,18 @@ def cpu_fw(fixed, cand, n, k, x0, budget_s, max_steps):
     from oracle import mac_oracle as orc
     mac = orc.OracleMAC(fixed, cand, n, fw_fiedler_method="arpack")
     x, u, done = x0, float("inf"), 0
+    fs = []
     t0 = time.perf_counter()
     while done < max_steps:
         f, g = mac.problem(x)
+        fs.append(float(f))
         s = orc.solve_subset_box_lp(g, k)
         u = min(u, f + g @ (s - x))
         x = x + orc.naive_stepsize(done) * (s - x)
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
-    return done, time.perf_counter() - t0
+    return done, time.perf_counter() - t0, fs
 
 
 def threads_used():
@@ -137,7 +140,7 @@ def run_reference(args, rank, world):
     fixed, cand, n, k, x0 = make_problem(0)
     if args.warmup > 0:
         cpu_fw(fixed, cand, n, k, x0, 0.0, 1)  # one untimed iteration: imports, page-in
-    iters, secs = cpu_fw(fixed, cand, n, k, x0, args.cpu_budget, args.steps)
+    iters, secs, _ = cpu_fw(fixed, cand, n, k, x0, args.cpu_budget, args.steps)
     value = iters / secs
     sample = f"{iters} whole FW iterations of the same workload (time-boxed to {args.cpu_budget:.0f} s of the requested {args.steps})"
     line = {
@@ -180,6 +183,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
+    parity_failed, rel = False, []
     fixed, cand, n, k, x0 = make_problem(rank)  # one graph per GPU (seed = rank), fixed per-GPU work
     mac = MAC(fixed, cand, n, device=local_rank)
     h = mac._h
@@ -272,13 +276,22 @@ def run_ours(args, rank, local_rank, world):
     }
     if world == 1 and not args.no_cpu_baseline:
         fixed0, cand0, n0, k0, x00 = (fixed, cand, n, k, x0)
-        iters, secs = cpu_fw(fixed0, cand0, n0, k0, x00, args.cpu_baseline_budget, 3)
+        iters, secs, f_cpu = cpu_fw(fixed0, cand0, n0, k0, x00, args.cpu_baseline_budget, 3)
         line["cpu_baseline"] = {"value": iters / secs, "unit": UNIT, "cores": threads_used(), "kind": "port",
                                 "sample": f"{iters} whole FW iterations of the same workload (oracle, scipy ARPACK eigen-solve)"}
+        # self-check: the oracle's f_t (lambda2 of its own free-running iterates) against the timed device run's history
+        ncmp = min(len(f_cpu), K)
+        rel = [abs(float(info["f_hist"][i]) - f_cpu[i]) / abs(f_cpu[i]) for i in range(ncmp)]
+        line["parity_check"] = {"max_rel_err": max(rel) if rel else None, "iters_compared": ncmp, "tolerance": PARITY_TOL,
+                                "what": "lambda2(L(x_t)) of the timed device run vs the oracle's free-running FW loop from the same x_init"}
+        parity_failed = bool(rel) and max(rel) > PARITY_TOL
     print(json.dumps(line), flush=True)
     mac.close()
     if dist is not None:
         dist.destroy_process_group()
+    if world == 1 and not args.no_cpu_baseline and parity_failed:
+        print(f"bench: PARITY FAILURE: max relative error {max(rel):.3e} > {PARITY_TOL:g}", file=sys.stderr)
+        sys.exit(1)
 
 
 def main():

@@ -163,6 +163,12 @@ int macb_spmv_engine(macb_handle h, int engine);
  * (CUDA-graph engine); "" before the first solve.  The pointer stays valid for the life of the handle. */
 const char* macb_lanczos_kernel_name(macb_handle h);
 
+/* Measured L2 -> SM read bandwidth of `device` (-1: current): every SM streams a `bytes`-sized, L2-resident buffer
+ * `reps` times with 16-byte loads that bypass L1.  The Lanczos kernels' matrix is L2-resident at the BASELINE sizes, so
+ * this -- not the HBM copy bandwidth -- is the roofline that binds them (bench.py `roofline.l2`).  Measurement only;
+ * replaces nothing in the reference. */
+int macb_measure_l2_bandwidth(int device, int64_t bytes, int reps, double* gbs);
+
 /* cudaDeviceSynchronize on the handle's device. */
 int macb_device_sync(macb_handle h);
 

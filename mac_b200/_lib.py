@@ -80,6 +80,7 @@ def lib():
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_host_build_jds, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int32, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip])
+    _sig(L.macb_measure_l2_bandwidth, [C.c_int, C.c_int64, C.c_int, _dp])
     _sig(L.macb_version, [], C.c_char_p)
     _lib = L
     return L
@@ -95,6 +96,15 @@ def _i32(a):
 
 def _p(a, typ):
     return a.ctypes.data_as(typ) if a is not None and a.size else None
+
+
+def measure_l2_bandwidth(device=-1, nbytes=24 << 20, reps=20):
+    """GB/s of L2 -> SM reads (all SMs streaming an L2-resident buffer); see include/macb200.h."""
+    out = C.c_double()
+    rc = lib().macb_measure_l2_bandwidth(int(device), int(nbytes), int(reps), C.byref(out))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_measure_l2_bandwidth failed ({rc}): {lib().macb_last_error(None).decode()}")
+    return out.value
 
 
 class Handle:

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -25,6 +27,12 @@ using namespace macb;
 namespace {
 
 thread_local std::string g_create_error;
+
+// The persisting-L2 carve-out is a property of the device, not of a handle: keep the largest carve any live handle asked
+// for and hand it back only when the last pinning handle on that device goes away.
+std::mutex g_l2_mutex;
+struct L2Pin { int refs = 0; size_t carve = 0; };
+std::map<int, L2Pin> g_l2_pins;
 
 constexpr int kGraphSteps = 32;            // Lanczos steps per captured CUDA graph
 constexpr size_t kFlushBytes = 512u << 20; // > 126 MB L2
@@ -102,6 +110,7 @@ struct macb_ctx {
     int64_t* d_sj_chunk_slot = nullptr;
     double* d_sj_val = nullptr;
     int vec_batch = 5;             // gathers in flight per thread in k_lanczos_vec (3..8, chosen from the slots per thread)
+    bool l2_pinned = false;        // this handle holds a reference on the device's persisting-L2 carve-out
     bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
@@ -258,7 +267,19 @@ void build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, 
 void free_all(macb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->d_jval) cudaCtxResetPersistingL2Cache();   // the weights were pinned in the persisting part of L2 (setup_persist)
+    if (c->l2_pinned) {   // the weights were pinned in the persisting part of L2 (setup_persist)
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.num_bytes = 0;   // drop this stream's window; other handles' lines stay where they are
+        if (c->stream) cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        std::lock_guard<std::mutex> lk(g_l2_mutex);
+        L2Pin& pin = g_l2_pins[c->device];
+        if (--pin.refs <= 0) {
+            cudaCtxResetPersistingL2Cache();
+            pin = L2Pin{};
+        }
+        cudaGetLastError();
+    }
     if (c->lz_graph) cudaGraphExecDestroy(c->lz_graph);
     if (c->sel_graph) cudaGraphExecDestroy(c->sel_graph);
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
@@ -673,7 +694,18 @@ void setup_persist(macb_ctx* c) {
                     CK(cudaGetDeviceProperties(&prop, c->device));
                     const size_t bytes = std::min<size_t>((size_t)c->nnz * sizeof(double), (size_t)prop.accessPolicyMaxWindowSize);
                     const size_t carve = std::min<size_t>(bytes + (bytes >> 2), (size_t)prop.persistingL2CacheMaxSize);
-                    if (bytes > 0 && carve >= bytes && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                    bool carved = false;
+                    if (bytes > 0 && carve >= bytes) {
+                        std::lock_guard<std::mutex> lk(g_l2_mutex);
+                        L2Pin& pin = g_l2_pins[c->device];
+                        carved = carve <= pin.carve || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess;
+                        if (carved) {
+                            pin.carve = std::max(pin.carve, carve);
+                            pin.refs++;
+                            c->l2_pinned = true;
+                        }
+                    }
+                    if (carved) {
                         cudaStreamAttrValue attr;
                         memset(&attr, 0, sizeof(attr));
                         attr.accessPolicyWindow.base_ptr = c->d_jval;
@@ -739,12 +771,18 @@ void setup_persist(macb_ctx* c) {
 
 void ensure_basis(macb_ctx* c, int max_steps) {
     if (c->d_basis) return;
-    double gb = 8.0;
+    // Capacity (Lanczos steps per cycle; a cycle that exhausts it restarts from its Ritz vector): what the caller asked
+    // for, never more than n - 1 (the Krylov space on 1-perp is exhausted by then), within a memory budget of
+    // MACB_BASIS_GB (default 2 GB, and at most half of the free device memory) -- several handles may share one GPU.
+    double gb = 2.0;
     if (const char* env = getenv("MACB_BASIS_GB")) gb = atof(env);
-    int64_t by_mem = (int64_t)(gb * 1073741824.0 / (8.0 * c->ld)) - 1;
-    int64_t cap = std::max<int64_t>(2 * kGraphSteps, std::min<int64_t>(by_mem, 65536));
-    cap = (cap / kGraphSteps) * kGraphSteps;
-    (void)max_steps;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)16 << 30; }
+    const double budget = std::min(gb * 1073741824.0, 0.5 * (double)free_b);
+    const int64_t by_mem = (int64_t)(budget / (8.0 * c->ld)) - 2;
+    const int64_t want = std::max<int64_t>(1, std::min<int64_t>(max_steps > 0 ? max_steps : 20000, (int64_t)c->n - 1));
+    int64_t cap = std::max<int64_t>(2 * kGraphSteps, std::min<int64_t>(std::min<int64_t>(want, by_mem), 65536));
+    cap = ((cap + kGraphSteps - 1) / kGraphSteps) * kGraphSteps;
     c->basis_cap = cap;
     c->d_basis = dalloc<double>((size_t)(cap + 2) * c->ld);   // k_lanczos_vec writes u_{j+1} at the end of phase j
     c->d_alpha = dalloc<double>(cap + 1);
@@ -881,20 +919,38 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                 }
                 __builtin_ia32_pause();
             }
+            // Every exit from here on that is not a normal return stops the kernel, waits for it and records how far it
+            // wrote into the mapped coefficient array (the next solve re-poisons exactly that range).
+            auto abort_cycle = [&](const char* what) {
+                *(volatile int*)c->h_stop = 1;
+                cudaStreamSynchronize(c->stream);
+                c->ab_dirty = std::max(c->ab_dirty, std::max((int)((volatile int*)c->h_stop)[1], k_limit + 1));
+                throw ArgFail{what, MACB_ERR_STATE};
+            };
             if (kernel_done && std::isnan(ab[2 * need + 1])) {
-                CK(cudaStreamSynchronize(c->stream));  // surfaces launch/runtime errors
-                if (std::isnan(ab[2 * need + 1])) throw ArgFail{"macb_fiedler: Lanczos kernel ended early", MACB_ERR_STATE};
+                const cudaError_t se = cudaStreamSynchronize(c->stream);  // surfaces launch/runtime errors
+                if (se != cudaSuccess) {
+                    c->ab_dirty = std::max(c->ab_dirty, k_limit + 1);
+                    throw CudaFail{se, "cudaStreamSynchronize (Lanczos kernel)", __LINE__};
+                }
+                if (std::isnan(ab[2 * need + 1])) abort_cycle("macb_fiedler: Lanczos kernel ended early");
             }
             const double tw1 = us();
             t_wait += tw1 - tw0;
+            // The kernel publishes the entries with plain stores to mapped memory, one phase after the other; nothing orders
+            // them with respect to each other on the way to the host, so beta[need] being visible does not make the earlier
+            // entries visible: wait for every entry on its own (NaN = not there yet; a poisoned recurrence publishes +inf).
             for (int j = k_seen; j <= need; ++j) {
+                for (unsigned int spin = 1; std::isnan(ab[2 * j]) || std::isnan(ab[2 * j + 1]); ++spin) {
+                    if ((spin & 0xfffffu) == 0 && cudaStreamQuery(c->stream) != cudaErrorNotReady &&
+                        (std::isnan(ab[2 * j]) || std::isnan(ab[2 * j + 1])))
+                        abort_cycle("macb_fiedler: a Lanczos coefficient never reached the host");
+                    __builtin_ia32_pause();
+                }
                 c->h_alpha[j] = ab[2 * j];
                 c->h_beta[j] = ab[2 * j + 1];
-                if (!std::isfinite(c->h_alpha[j]) || !std::isfinite(c->h_beta[j])) {
-                    *(volatile int*)c->h_stop = 1;
-                    cudaStreamSynchronize(c->stream);
-                    throw ArgFail{"macb_fiedler: the Lanczos recurrence produced a non-finite coefficient", MACB_ERR_STATE};
-                }
+                if (!std::isfinite(c->h_alpha[j]) || !std::isfinite(c->h_beta[j]))
+                    abort_cycle("macb_fiedler: the Lanczos recurrence produced a non-finite coefficient");
             }
             k_seen = std::max(k_seen, need + 1);
             int k = need;
@@ -904,7 +960,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
                     invariant = true;
                     break;
                 }
-            if (k == 0) throw ArgFail{"macb_fiedler: Lanczos made no progress", MACB_ERR_STATE};
+            if (k == 0) abort_cycle("macb_fiedler: Lanczos made no progress");
             const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k,
                                                         invariant ? std::numeric_limits<double>::infinity() : theta_prev, theta_delta);
             s.resize(k);
@@ -1147,6 +1203,15 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
     if (!st) st = c->d_sel_state;
     PhaseTimer pt(c, MACB_T_TOPK);
     const int64_t m = c->m;
+    if (m == 0) {   // nothing to select from: no selection, dual term 0 (the header allows m = 0 handles)
+        k_sel_init<<<1, kBlock, 0, c->stream>>>(st, 0ll);
+        k_clear_lp_scalars<<<1, 1, 0, c->stream>>>(c->d_sc);
+        c->c_launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_sel_state, st, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
+        if (!defer) CK(cudaStreamSynchronize(c->stream));
+        return;
+    }
     const int grid = c->grid_for(m);
     k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
     c->c_launches++;
@@ -1186,7 +1251,7 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
 // ties at the k-th value straddle the budget.
 bool topk_fixup(macb_ctx* c, const double* g, const double* x, int64_t k, uint8_t* sel, SelState* st = nullptr) {
     if (!st) st = c->d_sel_state;
-    if (!(k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining)) return false;
+    if (c->m == 0 || !(k > 0 && c->h_sel_state->eq_total != c->h_sel_state->remaining)) return false;
     const int64_t m = c->m;
     const int grid = c->grid_for(m);
     int64_t chunk = (m + grid - 1) / grid;
@@ -1758,6 +1823,46 @@ const char* macb_lanczos_kernel_name(macb_handle h) {
         case 4: return h->small_v2 ? "k_lanczos_small2" : "k_lanczos_small";
         case 3: return "k_lanczos_slots";
         default: return "k_lanczos_persist";
+    }
+}
+
+int macb_measure_l2_bandwidth(int device, int64_t bytes, int reps, double* gbs) {
+    if (bytes < (1 << 20) || reps < 1 || !gbs) return MACB_ERR_ARG;
+    try {
+        if (device >= 0) CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaGetDeviceProperties(&prop, dev));
+        const int64_t n16 = bytes / 16;
+        double2* buf = nullptr;
+        double* sink = nullptr;
+        CK(cudaMalloc(&buf, (size_t)n16 * 16));
+        CK(cudaMalloc(&sink, 8));
+        CK(cudaMemset(buf, 0, (size_t)n16 * 16));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        const int grid = prop.multiProcessorCount;
+        k_l2_read<<<grid, 1024>>>(buf, n16, 2, sink);   // warm-up: brings the buffer into L2
+        CK(cudaEventRecord(e0));
+        k_l2_read<<<grid, 1024>>>(buf, n16, reps, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        *gbs = (double)grid * reps * (double)(n16 * 16) / ((double)ms * 1e-3) / 1e9;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(buf);
+        cudaFree(sink);
+        return MACB_OK;
+    } catch (const CudaFail& e) {
+        char b[256];
+        snprintf(b, sizeof(b), "macb_measure_l2_bandwidth: CUDA error %d (%s)", (int)e.e, cudaGetErrorString(e.e));
+        g_create_error = b;
+        cudaGetLastError();
+        return MACB_ERR_CUDA;
     }
 }
 

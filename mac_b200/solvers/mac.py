@@ -22,10 +22,11 @@ from ..utils.rounding import round_madow, round_nearest
 class MAC:
     @dataclass
     class Cache:
-        """Problem data cache (mac.py:17-20).  In the reference it is never populated
-        (mac.py:126-127 stores the *input* Q); here `use_cache=True` warm-starts each
-        eigen-solve from the previous Fiedler vector -- same converged pair, fewer steps."""
+        """Problem data cache (mac.py:17-20).  In the reference it is never populated (mac.py:126-127
+        stores the *input* Q), so `use_cache=True` and `False` give bit-identical results there; the
+        same holds here.  Real warm starts are the separate, opt-in `warm_start=True`."""
         Q: Optional[np.ndarray] = None
+        warm: bool = False
 
     def __init__(self, fixed_edges, candidate_edges, num_nodes, fiedler_method="tracemin_lu", fiedler_tol=1e-8,
                  min_selection_weight_tol=1e-10, device=-1, fiedler_max_steps=0):
@@ -84,8 +85,10 @@ class MAC:
 
     def problem(self, x, cache=None):
         """mac.py:104-128: (lambda2(L(x)), supergradient).  As in the reference the FW-side solve
-        always runs at tol 1e-8 (mac.py:115 does not forward fiedler_tol)."""
-        warm = cache is not None and cache.Q is not None
+        always runs at tol 1e-8 (mac.py:115 does not forward fiedler_tol) and `cache` does not change
+        the result (mac.py:126-127 never populates it); `cache.warm = True` (an addition) warm-starts
+        the solve from the previous Fiedler vector on the device."""
+        warm = cache is not None and bool(getattr(cache, "warm", False)) and cache.Q is not None
         self._h.set_x(x, self.min_selection_weight_tol)
         f, _, info = self._h.fiedler(tol=1e-8, max_steps=self.fiedler_max_steps, warm=warm, want_vector=False)
         gradf = self._h.gradient()
@@ -98,19 +101,22 @@ class MAC:
         """The LP oracle on the gradient of the last `problem` call, without a host round trip."""
         return self._h.topk(k)
 
-    def frank_wolfe(self, k, x_init, max_iters=5, relative_duality_gap_tol=1e-4, grad_norm_tol=1e-8, use_cache=False):
+    def frank_wolfe(self, k, x_init, max_iters=5, relative_duality_gap_tol=1e-4, grad_norm_tol=1e-8, warm_start=False):
         """frank_wolfe(initial=x_init, problem=self.problem, solve_lp=top-k) on the device
         (frankwolfe.py:10-79 as mac.py:196-200 calls it).  Returns (w, u, info)."""
         w, u, info = self._h.fw_run(k, x_init, max_iters, relative_duality_gap_tol, grad_norm_tol, fiedler_tol=1e-8,
                                     min_sel_tol=self.min_selection_weight_tol,
-                                    fiedler_max_steps=self.fiedler_max_steps, warm=use_cache)
+                                    fiedler_max_steps=self.fiedler_max_steps, warm=warm_start)
         self.last_info = info
         return w, u, info
 
     def solve(self, k, x_init=None, rounding="nearest", fallback=False, max_iters=5, relative_duality_gap_tol=1e-4,
               grad_norm_tol=1e-8, random_rounding_max_iters=1, verbose=False, return_rounding_time=False,
-              use_cache=False):
-        """mac.py:130-225.  Returns (rounded, unrounded, upper_bound[, rounding_time])."""
+              use_cache=False, warm_start=False):
+        """mac.py:130-225.  Returns (rounded, unrounded, upper_bound[, rounding_time]).
+        `use_cache` is accepted and, exactly as in the reference, does not change the
+        result; `warm_start=True` (an addition) starts every eigen-solve after the first from the
+        previous Fiedler vector."""
         m = len(self.weights)
         if k >= m:  # mac.py:173-180
             result = np.ones(m)
@@ -119,7 +125,7 @@ class MAC:
             return result, result, self.evaluate_objective(np.ones(m))
         assert len(x_init) == m  # mac.py:183
         x_init = np.asarray(x_init, dtype=float)
-        w, u, info = self.frank_wolfe(k, x_init, max_iters, relative_duality_gap_tol, grad_norm_tol, use_cache)
+        w, u, info = self.frank_wolfe(k, x_init, max_iters, relative_duality_gap_tol, grad_norm_tol, warm_start)
         if verbose:
             for i, (f, ub) in enumerate(zip(info["f_hist"], info["u_hist"])):
                 print(f"iter {i}: f = {f:.12g}, upper = {ub:.12g}")

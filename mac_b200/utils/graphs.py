@@ -18,7 +18,10 @@ Edge = namedtuple("Edge", ["i", "j", "weight"])
 
 def edges_to_arrays(edges):
     """list[Edge] (or an (i, j, w) array triple) -> (int32[E], int32[E], float64[E])."""
-    if isinstance(edges, tuple) and len(edges) == 3 and not isinstance(edges, Edge) and hasattr(edges[0], "__len__"):
+    # array triple only when the three members are arrays / plain lists -- a tuple of exactly three Edge tuples is an
+    # edge list like any other iterable of Edge (the reference accepts any iterable)
+    if (isinstance(edges, tuple) and len(edges) == 3 and not isinstance(edges, Edge)
+            and all(isinstance(a, (np.ndarray, list)) for a in edges)):
         i, j, w = edges
         return np.asarray(i, dtype=np.int32), np.asarray(j, dtype=np.int32), np.asarray(w, dtype=np.float64)
     if len(edges) == 0:
