@@ -110,6 +110,10 @@ struct macb_ctx {
     int64_t* d_sj_chunk_slot = nullptr;
     double* d_sj_val = nullptr;
     int vec_batch = 5;             // gathers in flight per thread in k_lanczos_vec (3..8, chosen from the slots per thread)
+    bool pipe = true;              // k_lanczos_pipe (pipelined recurrence, reduction off the critical path) instead of k_lanczos_vec
+    size_t pipe_smem = 0;
+    bool sect_joint = false;       // d_sect[1] points into d_sect[0]'s allocation
+    double* d_zprev = nullptr;     // z_{j-1} across launches of k_lanczos_pipe
     bool l2_pinned = false;        // this handle holds a reference on the device's persisting-L2 carve-out
     bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
     bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
@@ -285,9 +289,9 @@ void free_all(macb_ctx* c) {
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
-                     c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
+                     c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->sect_joint ? nullptr : c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
                      c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec, c->d_sj_chunk_row, c->d_sj_chunk_jd, c->d_sj_jd,
-                     c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0};
+                     c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0, c->d_zprev};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
@@ -447,6 +451,27 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
                     c->d_diag, c->d_jrow};
         void* params[] = {&a, &J};
         void* fn = c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>;
+        if (c->jds_vec && c->pipe) {
+            LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, nullptr};
+            void* pparams[] = {&a, &J, &P};
+            void* pf;
+            switch (c->vec_batch) {
+                case 3: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 3> : (void*)k_lanczos_pipe<false, 3>; break;
+                case 4: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 4> : (void*)k_lanczos_pipe<false, 4>; break;
+                case 6: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 6> : (void*)k_lanczos_pipe<false, 6>; break;
+                case 7: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 7> : (void*)k_lanczos_pipe<false, 7>; break;
+                case 8: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 8> : (void*)k_lanczos_pipe<false, 8>; break;
+                default: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 5> : (void*)k_lanczos_pipe<false, 5>; break;
+            }
+            CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
+            if (c->bench_time_iters) CK(cudaEventRecord(c->lz1, c->stream));
+            c->c_launches += 1;
+            if (!async) {
+                c->c_spmv += nphases;
+                c->c_steps += nphases;
+            }
+            return;
+        }
         if (c->jds_vec) {
             switch (c->vec_batch) {
                 case 3: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 3> : (void*)k_lanczos_vec<false, 3>; break;
@@ -663,11 +688,17 @@ void setup_persist(macb_ctx* c) {
                 c->jd_stride = (int)stride;
                 c->slots_prod_cap = (int)cap4;
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
+                                c->pipe_smem = c->slots_smem;
+                c->pipe = !getenv("MACB_NO_PIPE");
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
 #define MACB_VEC_SMEM(VB_)                                                                                                                   \
     CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<false, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem)); \
-    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));  \
+    if (c->pipe) {                                                                                                                        \
+        CK(cudaFuncSetAttribute((const void*)k_lanczos_pipe<false, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->pipe_smem)); \
+        CK(cudaFuncSetAttribute((const void*)k_lanczos_pipe<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->pipe_smem));  \
+    }
                 MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
 #undef MACB_VEC_SMEM
                 {   // gathers in flight per thread: the batch size whose last batch of a step is fullest (see kernels.cuh)
@@ -687,6 +718,7 @@ void setup_persist(macb_ctx* c) {
                     }
                 }
                 c->jds_vec = !getenv("MACB_NO_VEC");
+                c->d_zprev = dalloc<double>((size_t)n);
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {
                     // keep the weights the Lanczos kernel streams every step (8 bytes per slot) in the persisting part of L2
@@ -754,8 +786,15 @@ void setup_persist(macb_ctx* c) {
     c->d_row_start = dalloc<int>(c->p_ncta + 1);
     CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->d_sect[0] = dalloc<double>((size_t)c->n * 4);
-    c->d_sect[1] = dalloc<double>((size_t)c->n * 4);
+    if (c->persist_v == 5 && c->jds_vec && c->pipe) {
+        // k_lanczos_pipe: one block of five rows of ld doubles (z buffers, u buffers, diagonal); see the kernel
+        c->d_sect[0] = dalloc<double>((size_t)c->ld * 5);
+        c->d_sect[1] = c->d_sect[0] + c->ld;
+        c->sect_joint = true;
+    } else {
+        c->d_sect[0] = dalloc<double>((size_t)c->n * 4);
+        c->d_sect[1] = dalloc<double>((size_t)c->n * 4);
+    }
     c->d_precs = dalloc<LzPartRec>((size_t)c->p_ncta * 2);
     c->d_pst = dalloc<LzPersistState>(1);
     CK(cudaMemsetAsync(c->d_pst, 0, sizeof(LzPersistState), c->stream));
@@ -1061,7 +1100,13 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     for (int restart = 0; restart < 64; ++restart) {
         // ---- (re)start
         const double* src = use_warm ? c->d_v : c->d_x0;
-        if (c->persist && c->persist_v == 5 && c->jds_vec) {
+        if (c->persist && c->persist_v == 5 && c->jds_vec && c->pipe) {
+            launch_spmv<0>(c, src, c->d_y);   // z_0 = L u_0 (the shift is applied by the init kernel)
+            c->c_launches++;
+            c->c_spmv++;
+            k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1],
+                                                                      c->d_basis, c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
+        } else if (c->persist && c->persist_v == 5 && c->jds_vec) {
             k_lz_vec_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_jrow, c->d_sect[0], c->d_sect[1], c->d_xrec,
                                                                      (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
         } else if (c->persist) {
@@ -1819,7 +1864,7 @@ const char* macb_lanczos_kernel_name(macb_handle h) {
     if (!h || !h->d_basis) return "";
     if (!h->persist) return "k_spmv+k_lanczos_b";
     switch (h->persist_v) {
-        case 5: return h->jds_vec ? "k_lanczos_vec" : "k_lanczos_jds";
+        case 5: return h->jds_vec ? (h->pipe ? "k_lanczos_pipe" : "k_lanczos_vec") : "k_lanczos_jds";
         case 4: return h->small_v2 ? "k_lanczos_small2" : "k_lanczos_small";
         case 3: return "k_lanczos_slots";
         default: return "k_lanczos_persist";

@@ -31,6 +31,7 @@ struct LzScalars {
     // gradient / LP
     double gnorm2, gdotx, gs_minus_x;
     int64_t nsel;
+    double shift;               // trace(L)/n: the spectral shift of the pipelined Lanczos kernel (k_assemble)
 };
 
 struct ReduceWS {
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(int n, const int* __restric
     const int lane = threadIdx.x & (W - 1);
     const int sub = (blockIdx.x * kBlock + threadIdx.x) / W;
     const int nsub = gridDim.x * kBlock / W;
-    double dmax = 0.0, cnt = 0.0;
+    double dmax = 0.0, cnt = 0.0, dsum = 0.0;
     const int rows_per_warp = 32 / W;
     for (int base = sub - (sub % rows_per_warp); base < n; base += nsub) {
         int row = base + (sub % rows_per_warp);
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(int n, const int* __restric
         if (row < n && lane == 0) {
             diag[row] = acc;
             dmax = fmax(dmax, acc);
+            dsum += acc;
         }
     }
     double v[1] = {dmax};
@@ -182,10 +184,13 @@ __global__ void __launch_bounds__(kBlock) k_assemble(int n, const int* __restric
     if (last_max) sc->lnorm = 2.0 * v[0];
     // second reduction (count) reuses the workspace after the first has fully completed in this block
     __syncthreads();
-    double c[1] = {cnt};
+    double c[2] = {cnt, dsum};
     ReduceWS ws2 = {ws.partials + (size_t)gridDim.x, ws.counter + 1};
-    bool last_cnt = grid_reduce<1, false>(c, ws2, sm, &flag);
-    if (last_cnt) sc->nnz_active = (int64_t)(c[0] + 0.5);
+    bool last_cnt = grid_reduce<2, false>(c, ws2, sm, &flag);
+    if (last_cnt) {
+        sc->nnz_active = (int64_t)(c[0] + 0.5);
+        sc->shift = c[1] / (double)n;
+    }
 }
 
 // ---- K1: CSR SpMV, W lanes per row, fused reductions ---------------------------------------------
@@ -1593,6 +1598,392 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
         a.st->cur = cur;
         a.st->beta_prev = beta_prev;
         a.st->usum_prev = usum_prev;
+    }
+}
+
+// ---- K3, pipelined form of k_lanczos_vec: the reduction leaves the critical path -------------------------------------------
+// k_lanczos_vec spends a quarter of every step in the grid-wide exchange of the four partial sums (three dependent L2 round
+// trips) plus the wait for the slowest CTA, because the coefficients alpha_j, beta_j of step j depend on z_j = L u_j, the
+// result of that very step's SpMV.  Here the recurrence is rearranged (Ghysels/Vanroose-style pipelining) so that the SpMV
+// and the reduction of a step are independent of each other:
+//     state per node:  u_j, u_{j-1},  z_j = L' u_j,  z_{j-1}            (L' = P L P - sigma I on 1-perp)
+//     step j:   sums (u_j.z_j, sum z_j, u_j.u_j, sum u_j) -> exchange          ... in flight during ...
+//               q_j = L' z_j                                                   ... this SpMV (gathers of z_j)
+//               u_{j+1} = k1 z_j + k2 u_j + k3 u_{j-1} + k4
+//               z_{j+1} = k1 q_j + k2 z_j + k3 z_{j-1} - sigma k4       (L' 1 = -sigma 1)
+// i.e. z_{j+1} = L' u_{j+1} is obtained by applying the three-term recurrence to the z's instead of by a product of its own.
+// The records of step j are pushed at the very START of the step (they depend only on what the update of step j-1 left in
+// registers) and are polled after the row sums, a whole SpMV later.
+//
+// Why the shift: the rounding errors d_j = z_j - L' u_j obey the same three-term recurrence as the Lanczos polynomials
+// evaluated at the shift, d_{j+1} = -((alpha_j - sigma) d_j + beta_j d_{j-1}) / beta_{j+1}.  At sigma = 0 that point lies outside
+// the spectrum of P L P on 1-perp and d_j grows like 1.25^j (measured: relative drift 1e-2 after 100 steps); with sigma inside
+// the support of the spectrum -- the mean diagonal entry, trace(L)/n -- the polynomials stay O(1): measured drift 5e-15 after
+// 260 steps at the headline size and 3e-14 after 4200 steps on city10000, Ritz values equal to plain Lanczos to 1e-15.
+// alpha_j is published with the shift added back, so T_k, the Rayleigh-Ritz step and the stopping rule are unchanged.
+//
+// No fences, no poison stores: "has the producer written this yet?" is answered by a one-bit GENERATION TAG in the least
+// significant mantissa bit of every published double.  The vector buffers alternate, so the buffer gathered in phase p was
+// last written two phases ago: tag(p) = (p >> 1) & 1 differs from the stale content's tag, and L2 (the point of coherence: all
+// these accesses bypass L1) never shows a reader an older value than one it has already seen.  The owner keeps the TAGGED
+// value in its own registers, so every CTA multiplies with the same z_j; the perturbation is one ulp of the gathered operand,
+// the size of the rounding error of the product it enters.  The records carry the same tag in the first of their four doubles
+// (a 32-byte sector is written and read as one transaction).  k_lanczos_vec needed a release fence per step (2 000 cycles
+// with a thousand stores in flight, measured) plus 8 + 32 bytes of poison per node and inbox slot to get the same guarantee.
+__device__ __forceinline__ double lz_tagged(double v, int tag) {
+    return __longlong_as_double((__double_as_longlong(v) & ~1ll) | (long long)tag);
+}
+__device__ __forceinline__ bool lz_tag_ok(double v, int tag) { return (int)(__double_as_longlong(v) & 1ll) == tag; }
+__device__ __forceinline__ double ld_f64_relaxed_if(const double* p, bool pred, double other) {
+    double v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, %3;\n\t@q ld.relaxed.gpu.global.f64 %0, [%1];\n\t}"
+                 : "=d"(v) : "l"(p), "r"((int)pred), "d"(other) : "memory");
+    return v;
+}
+
+template <bool SORTED, int VB>
+__device__ __forceinline__ void lz_gather_products_tagged(const double* __restrict__ U, const int* __restrict__ scol,
+                                                          const double* __restrict__ jval, int ns, int tid, int tag,
+                                                          double* __restrict__ prod, int* give_up) {
+    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
+    const double ok_zero = __longlong_as_double((long long)tag);   // what an unissued gather "returns": +0 with a valid tag
+    for (int b0 = tid; b0 < ns; b0 += VB * kPBlock) {
+        int c[VB];
+        double v[VB], wq[VB];
+#pragma unroll
+        for (int q = 0; q < VB; ++q) {
+            const int b = b0 + q * kPBlock;
+            c[q] = (b < ns) ? scol[b] : (int)0x80000000;
+        }
+#pragma unroll
+        for (int q = 0; q < VB; ++q) v[q] = ld_f64_relaxed_if(U + (c[q] & CM), c[q] >= 0, ok_zero);
+        // the weights of the whole batch are requested up front as well: loaded one by one next to their use they form a
+        // chain of VB dependent L2 latencies per batch
+#pragma unroll
+        for (int q = 0; q < VB; ++q) wq[q] = (c[q] >= 0) ? ld_stream(jval + b0 + q * kPBlock) : 0.0;
+#pragma unroll
+        for (int q = 0; q < VB; ++q) {
+            const int b = b0 + q * kPBlock;
+            if (!lz_tag_ok(v[q], tag)) {   // producer has not written yet: gather again (bounded: never hang the device)
+                unsigned int tries = 0;
+                do {
+                    __nanosleep(100);   // the producer is still in its row sums: do not fill the memory pipe with polls
+                    v[q] = ld_f64_relaxed_if(U + (c[q] & CM), true, ok_zero);
+                } while (!lz_tag_ok(v[q], tag) && ++tries < (1u << 16));
+                if (!lz_tag_ok(v[q], tag)) *give_up = 1;
+            }
+            if (b < ns) prod[SORTED ? ((c[q] >> 17) & 0x3fff) : b] = wq[q] * v[q];
+        }
+    }
+}
+
+// sum of the products of row `tid` along the jagged diagonals (eight per trip, predicated tail; jd is padded by 8 entries)
+__device__ __forceinline__ double lz_row_sum(const double* __restrict__ prod, const int* __restrict__ sjd, int len, int tid) {
+    const double* __restrict__ pt = prod + tid;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+    for (int d = 0; d < len; d += 8) {
+        const int4 o = *reinterpret_cast<const int4*>(sjd + d);
+        const int4 p = *reinterpret_cast<const int4*>(sjd + d + 4);
+        const int r = len - d;
+        a0 += pt[o.x];
+        a1 += (r > 1) ? pt[o.y] : 0.0;
+        a2 += (r > 2) ? pt[o.z] : 0.0;
+        a3 += (r > 3) ? pt[o.w] : 0.0;
+        a4 += (r > 4) ? pt[p.x] : 0.0;
+        a5 += (r > 5) ? pt[p.y] : 0.0;
+        a6 += (r > 6) ? pt[p.z] : 0.0;
+        a7 += (r > 7) ? pt[p.w] : 0.0;
+    }
+    return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+struct LzPipeArgs {
+    const LzScalars* sc;   // sc->shift = trace(L)/n (k_assemble)
+    double* zprev;         // [n] z_{j-1} of the CTA's rows across launches (engine numbering)
+    double* unused;
+    int* dev_stop;         // device-resident stop flag raised by the Rayleigh-Ritz CTA (may be nullptr)
+};
+
+// Start of a cycle: z_0 = L' u_0 comes from one plain SpMV (y = L u_0, caller numbering) so that the persistent kernel has no
+// special first step.  Buffer 0 <- z_0 tagged 0, buffer 1 and the inboxes <- NaN with the tag bit SET (never valid for the
+// phases 0 and 1 that read them first), basis row 0 <- u_0.
+__global__ void __launch_bounds__(kBlock) k_lz_pipe_init(int n, const double* __restrict__ src, const double* __restrict__ lsrc,
+                                                         const int* __restrict__ perm, const LzScalars* sc, double* __restrict__ z0,
+                                                         double* __restrict__ z1, double* __restrict__ basis0, double* __restrict__ xrec,
+                                                         int64_t nxrec, LzPersistState* st) {
+    const double nan1 = __longlong_as_double(0x7ff8000000000001ll);
+    const double sigma = sc->shift;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = perm[i];
+        const double u = src[c];
+        z0[i] = lz_tagged(fma(-sigma, u, lsrc[c]), 0);
+        z1[i] = nan1;
+        basis0[i] = u;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxrec; i += (int64_t)gridDim.x * blockDim.x) xrec[i] = nan1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->phase = 0;
+        st->cur = 0;
+        st->k1 = 0.0; st->k2 = 1.0; st->k3 = 0.0; st->k4 = 0.0;
+        st->beta_prev = 0.0;
+        st->usum_prev = 0.0;
+        st->bar = 0u;
+    }
+}
+
+template <bool SORTED, int VB>
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P) {
+    extern __shared__ double prod[];
+    __shared__ double sm[4 * kPWarps];
+    __shared__ double pollsum[4 * 8];
+    __shared__ double coef_s[8];          // k1, k2, k3, k4, alpha, beta of the phase being finished
+    __shared__ double beta_prev_s, usum_prev_s, sigma_s, inv_n_s;
+    __shared__ int stop_sm;
+    __shared__ int stop_in;
+    __shared__ int give_up;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
+    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
+    int* __restrict__ sjd = scol + J.prod_cap;
+    const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
+    const int sa = a.rp[ra], ns = a.rp[rb] - sa;
+    const bool has_row = tid < rb - ra;
+    const int row = ra + tid;
+    const int len = has_row ? J.jlen[row] : 0;
+    const double* __restrict__ jval = J.jval + sa;
+    for (int i = tid; i < ns; i += kPBlock)
+        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
+    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
+    int phase = a.st->phase;
+    int cur = a.st->cur;
+    if (tid == 0) {
+        give_up = 0;
+        stop_in = 0;
+        sigma_s = P.sc->shift;
+        inv_n_s = 1.0 / (double)a.n;
+        beta_prev_s = a.st->beta_prev;   // 1/beta of the last completed phase
+        usum_prev_s = a.st->usum_prev;
+    }
+    const unsigned int ncta = (unsigned int)a.ncta;
+    const int rows_warps = (rb - ra + 31) >> 5;
+    // the records are collected by warps that own no rows, one record per lane, when there are enough of those; otherwise by
+    // the last warp alone, after its own rows
+    const bool par_poll = rows_warps + (((int)ncta + 31) >> 5) <= kPWarps && ncta <= 256;
+    const int first_poll_warp = par_poll ? kPWarps - (((int)ncta + 31) >> 5) : kPWarps - 1;
+    // (never index a.sect[] with a run-time value: the whole parameter struct is then copied to LOCAL memory, 128 bytes per
+    // thread = 128 KB per CTA through a 48 KB L1, and every use becomes an L2 round trip -- 2 000 cycles per phase, measured)
+    // ONE base pointer for all per-row state in L2, rows of `ld` doubles: [0], [1] the two z buffers (= a.sect[0], a.sect[1]),
+    // [2], [3] u_j / u_{j-1} alternating like them (the basis is written with evict-first stores: reading it back is a DRAM
+    // round trip, measured), [4] the diagonal of L' = L - sigma I in engine order.  Fewer live pointers = no spills.
+    double* const S = a.sect[0];
+    const size_t ld = (size_t)a.ld;
+    if (has_row) __stcg(S + 4 * ld + row, J.diag[J.perm[row]] - P.sc->shift);
+
+    // No per-row state is carried in registers across the gather loop (left to the register allocator it is spilled to local
+    // memory there: 7 LDL + 4 STL per thread and phase through a 48 KB L1 = 2 200 cycles per phase, measured; parked in
+    // shared memory it shrinks that L1 to 8 KB and the remaining spills miss: pass 1 +2 000 cycles, measured).  Everything a
+    // row needs at the update is in L2 already and is fetched at the start of pass 2, under the row sums:
+    //   u_j = basis[phase], u_{j-1} = basis[phase-1], z_j = the published buffer, z_{j-1} = the buffer about to be overwritten.
+    {
+        double su = 0.0, sz = 0.0;
+        if (has_row) {
+            su = __ldcg(a.basis + (size_t)phase * a.ld + row);
+            sz = __ldcg(S + cur * ld + row);
+            __stcg(S + (2 + cur) * ld + row, su);
+            if (phase > 0) {   // z_{phase-1}, u_{phase-1} back where the loop expects them
+                __stcg(S + (cur ^ 1) * ld + row, __ldcg(P.zprev + row));
+                __stcg(S + (3 - cur) * ld + row, __ldcg(a.basis + (size_t)(phase - 1) * a.ld + row));
+            }
+        }
+        if (warp < rows_warps) {   // block sums of (u.z, sum z, u.u, sum u) for the records of the first phase of this launch
+            const double r = warp_sum4(su * sz, sz, su * su, su, lane);
+            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+        }
+    }
+    __syncthreads();
+
+    for (int it = 0; it < a.nphases; ++it) {
+        const double* __restrict__ Z = S + cur * ld;   // z_phase, published by every CTA for its own rows
+        const int tag = (phase >> 1) & 1, tag_next = ((phase + 1) >> 1) & 1;
+#ifdef MACB_PTIMING
+        const long long t_start = clock64();
+#endif
+        // ---- records of this phase: the last warp finishes the block sums and pushes them into every CTA's inbox
+        if (warp == kPWarps - 1) {
+            const double x0 = (lane < rows_warps) ? sm[lane] : 0.0, x1 = (lane < rows_warps) ? sm[kPWarps + lane] : 0.0,
+                         x2 = (lane < rows_warps) ? sm[2 * kPWarps + lane] : 0.0, x3 = (lane < rows_warps) ? sm[3 * kPWarps + lane] : 0.0;
+            const double r = warp_sum4(x0, x1, x2, x3, lane);
+            double q0 = __shfl_sync(0xffffffffu, r, 0), q1 = __shfl_sync(0xffffffffu, r, 8),
+                   q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
+            const double inf = __longlong_as_double(0x7ff0000000000000ll);
+            q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
+            if (*(volatile int*)&give_up) q0 = inf;   // poison alpha: the Rayleigh-Ritz side sees a non-finite value and reports it
+            if (blockIdx.x == 0) {
+                int stop_now = 0;
+                if (lane == 0) {
+                    if (a.stop) {   // host-mapped flag: fetched asynchronously during the previous phase (a PCIe read is slow)
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        stop_now = *(volatile int*)&stop_in;
+                    }
+                    if (P.dev_stop) {
+                        int ds;
+                        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(P.dev_stop) : "memory");
+                        stop_now |= ds;
+                    }
+                }
+                if (__shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
+                if (lane == 0 && a.stop)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(&stop_in)), "l"(a.stop) : "memory");
+            }
+            q0 = lz_tagged(q0, tag);
+            double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
+            for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
+        }
+        // ---- pass 1: products of the CTA's slots with the gathered z_phase
+        lz_gather_products_tagged<SORTED, VB>(Z, scol, jval, ns, tid, tag, prod, &give_up);
+        __syncthreads();
+#ifdef MACB_PTIMING
+        const long long t_p1 = clock64();
+        long long tb0 = 0, tb1 = 0, t_coef = 0;
+#endif
+        // ---- warps without rows collect the records of this phase, pushed a whole SpMV ago by everybody, and the last warp runs
+        // the (long, double-precision) coefficient chain for the whole CTA while the others sum their rows: when the row sums are
+        // done the coefficients sit in shared memory and nothing of the reduction is left on the critical path.  (In program
+        // order BEFORE the row sums so that the rows' state is not live -- and spilled -- across this register-hungry block.)
+        if (warp >= first_poll_warp) {
+            const double* const mine = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4 + (size_t)blockIdx.x * ncta * 4;
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            unsigned int spins = 0;
+#ifdef MACB_PTIMING
+            tb0 = clock64();
+#endif
+            if (par_poll) {
+                // one record per lane of the idle warps: ONE L2 round trip (a single warp walking 148 records pays one per
+                // record it handles: 1 000 - 1 500 cycles each under load, measured)
+                const unsigned int b = (unsigned int)(tid - first_poll_warp * 32);
+                while (true) {
+                    bool ok = true;
+                    if (b < ncta) {
+                        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(mine + (size_t)b * 4) : "memory");
+                        ok = lz_tag_ok(y0, tag);
+                    }
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > (1u << 18)) {
+                        give_up = 1;
+                        break;
+                    }
+                }
+                if (b == 0) stop_sm = (__double_as_longlong(y2) < 0) ? 1 : 0;
+                y2 = fabs(y2);
+                const double t = warp_sum4(y0, y1, y2, y3, lane);
+                if ((lane & 7) == 0) pollsum[(lane >> 3) * 8 + (warp - first_poll_warp)] = t;
+                asm volatile("bar.sync 1, %0;" ::"r"((kPWarps - first_poll_warp) * 32) : "memory");
+                y0 = y1 = y2 = y3 = 0.0;
+                for (int w = 0; w < kPWarps - first_poll_warp; ++w) {   // fixed order: identical totals on every CTA
+                    y0 += pollsum[w]; y1 += pollsum[8 + w]; y2 += pollsum[16 + w]; y3 += pollsum[24 + w];
+                }
+            } else {
+                int stop_seen = 0;
+                while (true) {
+                    bool ok = true;
+                    y0 = y1 = y2 = y3 = 0.0;
+                    for (unsigned int b = lane; b < ncta; b += 32) {
+                        double r0, r1, r2, r3;
+                        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
+                        ok = ok && lz_tag_ok(r0, tag);
+                        if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
+                        y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
+                    }
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > (1u << 18)) {
+                        give_up = 1;
+                        break;
+                    }
+                }
+                if (lane == 0) stop_sm = stop_seen;
+                const double t = warp_sum4(y0, y1, y2, y3, lane);
+                y0 = __shfl_sync(0xffffffffu, t, 0); y1 = __shfl_sync(0xffffffffu, t, 8);
+                y2 = __shfl_sync(0xffffffffu, t, 16); y3 = __shfl_sync(0xffffffffu, t, 24);
+            }
+#ifdef MACB_PTIMING
+            tb1 = clock64();
+#endif
+            if (tid == kPBlock - 32) {
+                const LzCoef c0 = lz_coefficients(y0, y1, y2, y3, (phase > 0) ? beta_prev_s : 0.0, usum_prev_s, inv_n_s);
+                coef_s[0] = c0.k1; coef_s[1] = c0.k2; coef_s[2] = c0.k3; coef_s[3] = c0.k4;
+                coef_s[4] = c0.alpha; coef_s[5] = c0.beta;
+                beta_prev_s = c0.binv;
+                usum_prev_s = y3;
+            }
+#ifdef MACB_PTIMING
+            t_coef = clock64();
+#endif
+        }
+        // ---- pass 2: q = L' z_phase for the CTA's rows; the row's state arrives from L2 under the row sum
+        double su = 0.0, sq = 0.0, sz = 0.0, szp = 0.0, qr = 0.0;
+        if (has_row) {
+            const double* __restrict__ Sr = S + row;
+            const double od = __ldcg(Sr + 4 * ld);
+            su = __ldcg(Sr + (2 + cur) * ld);
+            sz = __ldcg(Sr + cur * ld);
+            if (phase > 0) {
+                sq = __ldcg(Sr + (3 - cur) * ld);
+                szp = __ldcg(Sr + (cur ^ 1) * ld);   // the buffer about to be overwritten still holds z_{phase-1}
+            }
+            qr = -lz_row_sum(prod, sjd, len, tid);
+            qr = fma(od, sz, qr);
+        }
+#ifdef MACB_PTIMING
+        const long long t_rows = clock64();
+#endif
+        __syncthreads();
+#ifdef MACB_PTIMING
+        const long long t_bar = clock64();
+#endif
+        // ---- update of the CTA's rows, block sums for the next records
+        const int stop_all = stop_sm;
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+        if (has_row) {
+            const double k1 = coef_s[0], k2 = coef_s[1], k3 = coef_s[2], k4 = coef_s[3];
+            const double un = fma(k1, sz, fma(k2, su, k3 * sq)) + k4;
+            const double zn = lz_tagged(fma(k1, qr, fma(k2, sz, k3 * szp)) - sigma_s * k4, tag_next);
+            __stcg(S + (cur ^ 1) * ld + row, zn);
+            __stcg(S + (3 - cur) * ld + row, un);
+            __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
+            p1 = un * zn; p2 = zn; p3 = un * un; p4 = un;
+        }
+        if (warp < rows_warps) {
+            const double r = warp_sum4(p1, p2, p3, p4, lane);
+            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            const double alpha = coef_s[4] + sigma_s, beta = coef_s[5];
+            a.alpha[phase] = alpha;
+            a.beta[phase] = beta;
+            if (a.ab_host)
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(alpha), "d"(beta) : "memory");
+        }
+#ifdef MACB_PTIMING
+        if ((tid == 0 || tid == kPBlock - 32) && a.timing && it < 64) {
+            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 8;
+            if (tid == 0) { t[0] = t_start; t[1] = t_p1; t[2] = t_rows; t[6] = t_bar; t[7] = clock64(); }
+            else { t[3] = tb0; t[4] = tb1; t[5] = t_coef; }
+        }
+#endif
+        cur ^= 1;
+        ++phase;
+        __syncthreads();   // sm[] complete for the last warp; coef_s / stop_sm free for the next phase
+        if (stop_all) break;
+    }
+    // z_{phase-1} sits in the buffer the next update would overwrite; a later launch (resume) finds it in zprev
+    if (has_row && phase > 0) P.zprev[row] = __ldcg(S + (cur ^ 1) * ld + row);
+    if (blockIdx.x == 0 && tid == 0) {
+        a.st->phase = phase;
+        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
+        a.st->cur = cur;
+        a.st->beta_prev = beta_prev_s;
+        a.st->usum_prev = usum_prev_s;
     }
 }
 
