@@ -689,7 +689,11 @@ void setup_persist(macb_ctx* c) {
                 c->slots_prod_cap = (int)cap4;
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
                                 c->pipe_smem = c->slots_smem;
-                c->pipe = !getenv("MACB_NO_PIPE");
+                {   // k_lanczos_pipe wants its last ceil(ncta / 32) warps free of rows (they poll the exchange records)
+                    int maxrows = 0;
+                    for (int b = 0; b < ncta; ++b) maxrows = std::max(maxrows, rs[b + 1] - rs[b]);
+                    c->pipe = !getenv("MACB_NO_PIPE") && ncta <= 256 && maxrows <= (kPWarps - (ncta + 31) / 32) * 32;
+                }
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
                 CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
 #define MACB_VEC_SMEM(VB_)                                                                                                                   \

@@ -1677,11 +1677,12 @@ __device__ __forceinline__ void lz_gather_products_tagged(const double* __restri
     }
 }
 
-// sum of the products of row `tid` along the jagged diagonals (eight per trip, predicated tail; jd is padded by 8 entries)
-__device__ __forceinline__ double lz_row_sum(const double* __restrict__ prod, const int* __restrict__ sjd, int len, int tid) {
+// sum of the products of row `tid` along the jagged diagonals d0 <= d < len (d0 a multiple of 8; eight per trip, predicated
+// tail; jd is padded by 8 entries)
+__device__ __forceinline__ double lz_row_sum(const double* __restrict__ prod, const int* __restrict__ sjd, int len, int tid, int d0 = 0) {
     const double* __restrict__ pt = prod + tid;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
-    for (int d = 0; d < len; d += 8) {
+    for (int d = d0; d < len; d += 8) {
         const int4 o = *reinterpret_cast<const int4*>(sjd + d);
         const int4 p = *reinterpret_cast<const int4*>(sjd + d + 4);
         const int r = len - d;
@@ -1731,16 +1732,26 @@ __global__ void __launch_bounds__(kBlock) k_lz_pipe_init(int n, const double* __
     }
 }
 
+struct LzPipeShared {
+    double pollsum[4 * 8];
+    double coef[8];            // k1, k2, k3, k4, alpha, beta of the phase being finished
+    double beta_prev, usum_prev, sigma, inv_n;
+    int stop, give_up;
+};
+
+#define LZ_BAR(id) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(kPBlock) : "memory")
+
+// Host contract (setup_persist): every CTA has at most (kPWarps - ceil(ncta / 32)) * 32 rows, so that the last ceil(ncta / 32)
+// warps own no rows and can act as the polling warps.
 template <bool SORTED, int VB>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P) {
     extern __shared__ double prod[];
     __shared__ double sm[4 * kPWarps];
-    __shared__ double pollsum[4 * 8];
-    __shared__ double coef_s[8];          // k1, k2, k3, k4, alpha, beta of the phase being finished
-    __shared__ double beta_prev_s, usum_prev_s, sigma_s, inv_n_s;
-    __shared__ int stop_sm;
+    __shared__ LzPipeShared sh;
+    __shared__ unsigned short slen[kPBlock];   // row lengths (a global load here would put an L2 round trip -- 2 500 cycles under
+                                               // this kernel's own load, measured -- in front of every row sum)
+    __shared__ double hsum[256];          // partial row sums of the helper threads (long rows are split in two)
     __shared__ int stop_in;
-    __shared__ int give_up;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
     int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
     int* __restrict__ sjd = scol + J.prod_cap;
@@ -1748,7 +1759,6 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
     const int sa = a.rp[ra], ns = a.rp[rb] - sa;
     const bool has_row = tid < rb - ra;
     const int row = ra + tid;
-    const int len = has_row ? J.jlen[row] : 0;
     const double* __restrict__ jval = J.jval + sa;
     for (int i = tid; i < ns; i += kPBlock)
         scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
@@ -1756,42 +1766,46 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
     int phase = a.st->phase;
     int cur = a.st->cur;
     if (tid == 0) {
-        give_up = 0;
+        sh.give_up = 0;
         stop_in = 0;
-        sigma_s = P.sc->shift;
-        inv_n_s = 1.0 / (double)a.n;
-        beta_prev_s = a.st->beta_prev;   // 1/beta of the last completed phase
-        usum_prev_s = a.st->usum_prev;
+        sh.sigma = P.sc->shift;
+        sh.inv_n = 1.0 / (double)a.n;
+        sh.beta_prev = a.st->beta_prev;   // 1/beta of the last completed phase
+        sh.usum_prev = a.st->usum_prev;
     }
     const unsigned int ncta = (unsigned int)a.ncta;
     const int rows_warps = (rb - ra + 31) >> 5;
-    // the records are collected by warps that own no rows, one record per lane, when there are enough of those; otherwise by
-    // the last warp alone, after its own rows
-    const bool par_poll = rows_warps + (((int)ncta + 31) >> 5) <= kPWarps && ncta <= 256;
-    const int first_poll_warp = par_poll ? kPWarps - (((int)ncta + 31) >> 5) : kPWarps - 1;
-    // (never index a.sect[] with a run-time value: the whole parameter struct is then copied to LOCAL memory, 128 bytes per
-    // thread = 128 KB per CTA through a 48 KB L1, and every use becomes an L2 round trip -- 2 000 cycles per phase, measured)
+    const int poll_warps = ((int)ncta + 31) >> 5;
+    const int first_poll_warp = kPWarps - poll_warps;
+    // Long rows are split in two.  The rows are numbered by decreasing length, so row/thread 0 has the longest (twice the mean
+    // on an Erdos-Renyi graph) and its row sum, a chain of dependent shared-memory round trips, is what the whole CTA waits for
+    // at the end of pass 2.  The warps that neither own rows nor poll ("helpers", nhelp threads) take the diagonals d >= split
+    // of rows 0 .. nhelp-1; split = the length of row nhelp rounded up to 8, at least half the longest row.
+    const int nhelp = max(0, min(min((first_poll_warp - rows_warps) * 32, 256), rb - ra));
+    int split = 1 << 30;
+    if (nhelp > 0) {
+        const int lmax = ld_nc(J.jlen + ra), lcut = ld_nc(J.jlen + ra + min(nhelp, rb - ra - 1));
+        split = max((lcut + 7) & ~7, (((lmax + 1) >> 1) + 7) & ~7);
+    }
+    const int helper_row = tid - rows_warps * 32;   // >= 0 and < nhelp: this thread helps row `helper_row`
+    slen[tid] = (unsigned short)(has_row ? ld_nc(J.jlen + row) : 0);
     // ONE base pointer for all per-row state in L2, rows of `ld` doubles: [0], [1] the two z buffers (= a.sect[0], a.sect[1]),
     // [2], [3] u_j / u_{j-1} alternating like them (the basis is written with evict-first stores: reading it back is a DRAM
-    // round trip, measured), [4] the diagonal of L' = L - sigma I in engine order.  Fewer live pointers = no spills.
-    double* const S = a.sect[0];
-    const size_t ld = (size_t)a.ld;
-    if (has_row) __stcg(S + 4 * ld + row, J.diag[J.perm[row]] - P.sc->shift);
-
-    // No per-row state is carried in registers across the gather loop (left to the register allocator it is spilled to local
-    // memory there: 7 LDL + 4 STL per thread and phase through a 48 KB L1 = 2 200 cycles per phase, measured; parked in
-    // shared memory it shrinks that L1 to 8 KB and the remaining spills miss: pass 1 +2 000 cycles, measured).  Everything a
-    // row needs at the update is in L2 already and is fetched at the start of pass 2, under the row sums:
-    //   u_j = basis[phase], u_{j-1} = basis[phase-1], z_j = the published buffer, z_{j-1} = the buffer about to be overwritten.
+    // round trip, measured), [4] the diagonal of L' = L - sigma I in engine order.  (Never index a.sect[] with a run-time value:
+    // the whole parameter struct is then copied to LOCAL memory, 128 bytes per thread = 128 KB per CTA through a 48 KB L1, and
+    // every use becomes an L2 round trip -- 2 000 cycles per phase, measured.)
+#define LZS (a.sect[0])
+#define LZLD ((size_t)a.ld)
+    if (has_row) __stcg(LZS + 4 * LZLD + row, J.diag[J.perm[row]] - P.sc->shift);
     {
         double su = 0.0, sz = 0.0;
         if (has_row) {
             su = __ldcg(a.basis + (size_t)phase * a.ld + row);
-            sz = __ldcg(S + cur * ld + row);
-            __stcg(S + (2 + cur) * ld + row, su);
+            sz = __ldcg(LZS + cur * LZLD + row);
+            __stcg(LZS + (2 + cur) * LZLD + row, su);
             if (phase > 0) {   // z_{phase-1}, u_{phase-1} back where the loop expects them
-                __stcg(S + (cur ^ 1) * ld + row, __ldcg(P.zprev + row));
-                __stcg(S + (3 - cur) * ld + row, __ldcg(a.basis + (size_t)(phase - 1) * a.ld + row));
+                __stcg(LZS + (cur ^ 1) * LZLD + row, __ldcg(P.zprev + row));
+                __stcg(LZS + (3 - cur) * LZLD + row, __ldcg(a.basis + (size_t)(phase - 1) * a.ld + row));
             }
         }
         if (warp < rows_warps) {   // block sums of (u.z, sum z, u.u, sum u) for the records of the first phase of this launch
@@ -1802,10 +1816,11 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
     __syncthreads();
 
     for (int it = 0; it < a.nphases; ++it) {
-        const double* __restrict__ Z = S + cur * ld;   // z_phase, published by every CTA for its own rows
+        const double* __restrict__ Z = LZS + cur * LZLD;   // z_phase, published by every CTA for its own rows
         const int tag = (phase >> 1) & 1, tag_next = ((phase + 1) >> 1) & 1;
 #ifdef MACB_PTIMING
         const long long t_start = clock64();
+        long long t_p1 = 0, t_rows = 0, t_bar = 0, tb0 = 0, tb1 = 0;
 #endif
         // ---- records of this phase: the last warp finishes the block sums and pushes them into every CTA's inbox
         if (warp == kPWarps - 1) {
@@ -1816,7 +1831,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
                    q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
             q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
-            if (*(volatile int*)&give_up) q0 = inf;   // poison alpha: the Rayleigh-Ritz side sees a non-finite value and reports it
+            if (*(volatile int*)&sh.give_up) q0 = inf;   // poison alpha: the Rayleigh-Ritz side sees a non-finite value and reports it
             if (blockIdx.x == 0) {
                 int stop_now = 0;
                 if (lane == 0) {
@@ -1839,152 +1854,143 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
             for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
         }
         // ---- pass 1: products of the CTA's slots with the gathered z_phase
-        lz_gather_products_tagged<SORTED, VB>(Z, scol, jval, ns, tid, tag, prod, &give_up);
-        __syncthreads();
-#ifdef MACB_PTIMING
-        const long long t_p1 = clock64();
-        long long tb0 = 0, tb1 = 0, t_coef = 0;
-#endif
-        // ---- warps without rows collect the records of this phase, pushed a whole SpMV ago by everybody, and the last warp runs
-        // the (long, double-precision) coefficient chain for the whole CTA while the others sum their rows: when the row sums are
-        // done the coefficients sit in shared memory and nothing of the reduction is left on the critical path.  (In program
-        // order BEFORE the row sums so that the rows' state is not live -- and spilled -- across this register-hungry block.)
+        lz_gather_products_tagged<SORTED, VB>(Z, scol, jval, ns, tid, tag, prod, &sh.give_up);
+
+        // From here to the update the polling warps and the row warps run DIFFERENT code between the same two CTA barriers,
+        // so that what a row thread keeps in registers (its state, requested from L2 before the first barrier) is not live
+        // across the register-hungry polling / coefficient code: inlined into one path the allocator spills it to local memory.
+        // Everything needed from L2 is requested BEFORE the barrier that ends pass 1: an L2 round trip costs ~2 500 cycles
+        // while the other SMs are gathering -- as long as the row sums and the update together.
         if (warp >= first_poll_warp) {
+            // ---- polling warps: this lane's record of the exchange (pushed a whole SpMV ago by everybody); one record per lane
+            // = ONE L2 round trip.  The last lane-0 then runs the (long, double-precision) coefficient chain for the whole CTA
+            // while the others sum their rows: nothing of the reduction is left on the critical path.
             const double* const mine = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4 + (size_t)blockIdx.x * ncta * 4;
-            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-            unsigned int spins = 0;
+            const unsigned int pb = (unsigned int)(tid - first_poll_warp * 32);
+            double y0 = __longlong_as_double((long long)tag), y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            if (pb < ncta)
+                asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(mine + (size_t)pb * 4) : "memory");
+            LZ_BAR(2);
 #ifdef MACB_PTIMING
             tb0 = clock64();
 #endif
-            if (par_poll) {
-                // one record per lane of the idle warps: ONE L2 round trip (a single warp walking 148 records pays one per
-                // record it handles: 1 000 - 1 500 cycles each under load, measured)
-                const unsigned int b = (unsigned int)(tid - first_poll_warp * 32);
-                while (true) {
-                    bool ok = true;
-                    if (b < ncta) {
-                        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                     : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(mine + (size_t)b * 4) : "memory");
-                        ok = lz_tag_ok(y0, tag);
-                    }
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    if (++spins > (1u << 18)) {
-                        give_up = 1;
-                        break;
-                    }
+            unsigned int spins = 0;
+            while (true) {
+                const bool ok = (pb >= ncta) || lz_tag_ok(y0, tag);
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > (1u << 18)) {
+                    sh.give_up = 1;
+                    break;
                 }
-                if (b == 0) stop_sm = (__double_as_longlong(y2) < 0) ? 1 : 0;
-                y2 = fabs(y2);
-                const double t = warp_sum4(y0, y1, y2, y3, lane);
-                if ((lane & 7) == 0) pollsum[(lane >> 3) * 8 + (warp - first_poll_warp)] = t;
-                asm volatile("bar.sync 1, %0;" ::"r"((kPWarps - first_poll_warp) * 32) : "memory");
-                y0 = y1 = y2 = y3 = 0.0;
-                for (int w = 0; w < kPWarps - first_poll_warp; ++w) {   // fixed order: identical totals on every CTA
-                    y0 += pollsum[w]; y1 += pollsum[8 + w]; y2 += pollsum[16 + w]; y3 += pollsum[24 + w];
+                if (!ok)
+                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(mine + (size_t)pb * 4) : "memory");
+            }
+            if (pb == 0) sh.stop = (__double_as_longlong(y2) < 0) ? 1 : 0;
+            if (pb >= ncta) y0 = 0.0;
+            y2 = fabs(y2);
+            const double t = warp_sum4(y0, y1, y2, y3, lane);
+            if ((lane & 7) == 0) sh.pollsum[(lane >> 3) * 8 + (warp - first_poll_warp)] = t;
+            asm volatile("bar.sync 1, %0;" ::"r"(poll_warps * 32) : "memory");
+            if (tid == kPBlock - 32) {
+                double P1 = 0.0, P2 = 0.0, P3 = 0.0, P4 = 0.0;
+                for (int w = 0; w < poll_warps; ++w) {   // fixed order: identical totals on every CTA
+                    P1 += sh.pollsum[w]; P2 += sh.pollsum[8 + w]; P3 += sh.pollsum[16 + w]; P4 += sh.pollsum[24 + w];
                 }
-            } else {
-                int stop_seen = 0;
-                while (true) {
-                    bool ok = true;
-                    y0 = y1 = y2 = y3 = 0.0;
-                    for (unsigned int b = lane; b < ncta; b += 32) {
-                        double r0, r1, r2, r3;
-                        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                     : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
-                        ok = ok && lz_tag_ok(r0, tag);
-                        if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
-                        y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
-                    }
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    if (++spins > (1u << 18)) {
-                        give_up = 1;
-                        break;
-                    }
-                }
-                if (lane == 0) stop_sm = stop_seen;
-                const double t = warp_sum4(y0, y1, y2, y3, lane);
-                y0 = __shfl_sync(0xffffffffu, t, 0); y1 = __shfl_sync(0xffffffffu, t, 8);
-                y2 = __shfl_sync(0xffffffffu, t, 16); y3 = __shfl_sync(0xffffffffu, t, 24);
+                const LzCoef c0 = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? sh.beta_prev : 0.0, sh.usum_prev, sh.inv_n);
+                sh.coef[0] = c0.k1; sh.coef[1] = c0.k2; sh.coef[2] = c0.k3; sh.coef[3] = c0.k4;
+                sh.coef[4] = c0.alpha; sh.coef[5] = c0.beta;
+                sh.beta_prev = c0.binv;
+                sh.usum_prev = P4;
             }
 #ifdef MACB_PTIMING
             tb1 = clock64();
 #endif
-            if (tid == kPBlock - 32) {
-                const LzCoef c0 = lz_coefficients(y0, y1, y2, y3, (phase > 0) ? beta_prev_s : 0.0, usum_prev_s, inv_n_s);
-                coef_s[0] = c0.k1; coef_s[1] = c0.k2; coef_s[2] = c0.k3; coef_s[3] = c0.k4;
-                coef_s[4] = c0.alpha; coef_s[5] = c0.beta;
-                beta_prev_s = c0.binv;
-                usum_prev_s = y3;
+            LZ_BAR(3);
+        } else {
+            // ---- row warps (and helpers): the row's state from L2 (u_j, u_{j-1}, z_j, z_{j-1}, diagonal; not carried in
+            // registers across the gather loop, where it would be spilled), the row sums, the update
+            double su = 0.0, sq = 0.0, sz = 0.0, szp = 0.0, qr = 0.0, od = 0.0;
+            if (has_row) {
+                const double* __restrict__ Sr = LZS + row;
+                od = __ldcg(Sr + 4 * LZLD);
+                su = __ldcg(Sr + (2 + cur) * LZLD);
+                sz = __ldcg(Sr + cur * LZLD);
+                if (phase > 0) {
+                    sq = __ldcg(Sr + (3 - cur) * LZLD);
+                    szp = __ldcg(Sr + (cur ^ 1) * LZLD);   // the buffer about to be overwritten still holds z_{phase-1}
+                }
+            }
+            LZ_BAR(2);
+#ifdef MACB_PTIMING
+            t_p1 = clock64();
+#endif
+            // ---- pass 2: the products of the CTA's rows, summed along the jagged diagonals
+            bool helped = false;
+            if (has_row) {
+                const int len = slen[tid];
+                qr = lz_row_sum(prod, sjd, min(len, split), tid);
+                helped = (tid < nhelp) && (len > split);
+            } else if (helper_row >= 0 && helper_row < nhelp) {
+                const int len = slen[helper_row];
+                if (len > split) hsum[helper_row] = lz_row_sum(prod, sjd, len, helper_row, split);
             }
 #ifdef MACB_PTIMING
-            t_coef = clock64();
+            t_rows = clock64();
 #endif
-        }
-        // ---- pass 2: q = L' z_phase for the CTA's rows; the row's state arrives from L2 under the row sum
-        double su = 0.0, sq = 0.0, sz = 0.0, szp = 0.0, qr = 0.0;
-        if (has_row) {
-            const double* __restrict__ Sr = S + row;
-            const double od = __ldcg(Sr + 4 * ld);
-            su = __ldcg(Sr + (2 + cur) * ld);
-            sz = __ldcg(Sr + cur * ld);
-            if (phase > 0) {
-                sq = __ldcg(Sr + (3 - cur) * ld);
-                szp = __ldcg(Sr + (cur ^ 1) * ld);   // the buffer about to be overwritten still holds z_{phase-1}
+            LZ_BAR(3);
+#ifdef MACB_PTIMING
+            t_bar = clock64();
+#endif
+            // ---- update of the CTA's rows, block sums for the next records
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+            if (has_row) {
+                const double k1 = sh.coef[0], k2 = sh.coef[1], k3 = sh.coef[2], k4 = sh.coef[3];
+                if (helped) qr += hsum[tid];
+                qr = fma(od, sz, -qr);   // (L' z_phase)[row]
+                const double un = fma(k1, sz, fma(k2, su, k3 * sq)) + k4;
+                const double zn = lz_tagged(fma(k1, qr, fma(k2, sz, k3 * szp)) - sh.sigma * k4, tag_next);
+                __stcg(LZS + (cur ^ 1) * LZLD + row, zn);
+                __stcg(LZS + (3 - cur) * LZLD + row, un);
+                __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
+                p1 = un * zn; p2 = zn; p3 = un * un; p4 = un;
             }
-            qr = -lz_row_sum(prod, sjd, len, tid);
-            qr = fma(od, sz, qr);
-        }
-#ifdef MACB_PTIMING
-        const long long t_rows = clock64();
-#endif
-        __syncthreads();
-#ifdef MACB_PTIMING
-        const long long t_bar = clock64();
-#endif
-        // ---- update of the CTA's rows, block sums for the next records
-        const int stop_all = stop_sm;
-        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
-        if (has_row) {
-            const double k1 = coef_s[0], k2 = coef_s[1], k3 = coef_s[2], k4 = coef_s[3];
-            const double un = fma(k1, sz, fma(k2, su, k3 * sq)) + k4;
-            const double zn = lz_tagged(fma(k1, qr, fma(k2, sz, k3 * szp)) - sigma_s * k4, tag_next);
-            __stcg(S + (cur ^ 1) * ld + row, zn);
-            __stcg(S + (3 - cur) * ld + row, un);
-            __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
-            p1 = un * zn; p2 = zn; p3 = un * un; p4 = un;
-        }
-        if (warp < rows_warps) {
-            const double r = warp_sum4(p1, p2, p3, p4, lane);
-            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
-        }
-        if (blockIdx.x == 0 && tid == 0) {
-            const double alpha = coef_s[4] + sigma_s, beta = coef_s[5];
-            a.alpha[phase] = alpha;
-            a.beta[phase] = beta;
-            if (a.ab_host)
-                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(alpha), "d"(beta) : "memory");
+            if (warp < rows_warps) {
+                const double r = warp_sum4(p1, p2, p3, p4, lane);
+                if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+            }
+            if (blockIdx.x == 0 && tid == 0) {
+                const double alpha = sh.coef[4] + sh.sigma, beta = sh.coef[5];
+                a.alpha[phase] = alpha;
+                a.beta[phase] = beta;
+                if (a.ab_host)
+                    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(alpha), "d"(beta) : "memory");
+            }
         }
 #ifdef MACB_PTIMING
         if ((tid == 0 || tid == kPBlock - 32) && a.timing && it < 64) {
             long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 8;
             if (tid == 0) { t[0] = t_start; t[1] = t_p1; t[2] = t_rows; t[6] = t_bar; t[7] = clock64(); }
-            else { t[3] = tb0; t[4] = tb1; t[5] = t_coef; }
+            else { t[3] = tb0; t[4] = tb1; t[5] = tb1; }
         }
 #endif
         cur ^= 1;
         ++phase;
-        __syncthreads();   // sm[] complete for the last warp; coef_s / stop_sm free for the next phase
-        if (stop_all) break;
+        __syncthreads();   // sm[] complete for the last warp; sh.coef / sh.stop free for the next phase
+        if (sh.stop) break;
     }
     // z_{phase-1} sits in the buffer the next update would overwrite; a later launch (resume) finds it in zprev
-    if (has_row && phase > 0) P.zprev[row] = __ldcg(S + (cur ^ 1) * ld + row);
+    if (has_row && phase > 0) P.zprev[row] = __ldcg(LZS + (cur ^ 1) * LZLD + row);
     if (blockIdx.x == 0 && tid == 0) {
         a.st->phase = phase;
         if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
         a.st->cur = cur;
-        a.st->beta_prev = beta_prev_s;
-        a.st->usum_prev = usum_prev_s;
+        a.st->beta_prev = sh.beta_prev;
+        a.st->usum_prev = sh.usum_prev;
     }
+#undef LZS
+#undef LZLD
 }
 
 // ---- K3, single-CTA form for small graphs (pose graphs with n up to 3072 nodes, 12288 slots) -------------

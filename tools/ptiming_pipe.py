@@ -26,12 +26,10 @@ L.macb_debug_ptiming(mac._h._h, raw.ctypes.data_as(C.c_void_p), C.byref(ncta))
 t = raw[:64 * ncta.value * 8].reshape(64, ncta.value, 8)[4:60].astype(np.float64)
 def st(x): return "mean %.0f  min-cta %.0f  max-cta %.0f" % (x.mean(), x.min(axis=1).mean(), x.max(axis=1).mean())
 print("ncta", ncta.value)
-print("pass 1 (gathers + barrier)        ", st(t[:, :, 1] - t[:, :, 0]))
-print("pass 2 (state loads + row sum, t0) ", st(t[:, :, 2] - t[:, :, 1]))
-print("last warp: pass-1 barrier -> poll   ", st(t[:, :, 3] - t[:, :, 1]))
-print("last warp: poll                    ", st(t[:, :, 4] - t[:, :, 3]))
-print("last warp: coefficient chain       ", st(t[:, :, 5] - t[:, :, 4]))
-print("rows done -> barrier B passed (t0) ", st(t[:, :, 6] - t[:, :, 2]))
-print("update, stores, block sums (t0)    ", st(t[:, :, 7] - t[:, :, 6]))
-print("end -> next start (barrier C)      ", st(t[1:, :, 0] - t[:-1, :, 7]))
-print("whole phase (start -> start)       ", st(np.diff(t[:, :, 0], axis=0)))
+print("pass 1 (gathers + barrier A)        ", st(t[:, :, 1] - t[:, :, 0]))
+print("pass 2 (row sum, thread 0)          ", st(t[:, :, 2] - t[:, :, 1]))
+print("poll warps: after barrier A -> coef  ", st(t[:, :, 4] - t[:, :, 3]))
+print("rows done -> barrier B passed (t0)  ", st(t[:, :, 6] - t[:, :, 2]))
+print("update, stores, block sums (t0)     ", st(t[:, :, 7] - t[:, :, 6]))
+print("end -> next start (barrier C)       ", st(t[1:, :, 0] - t[:-1, :, 7]))
+print("whole phase (start -> start)        ", st(np.diff(t[:, :, 0], axis=0)))
