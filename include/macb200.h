@@ -169,6 +169,14 @@ const char* macb_lanczos_kernel_name(macb_handle h);
  * replaces nothing in the reference. */
 int macb_measure_l2_bandwidth(int device, int64_t bytes, int reps, double* gbs);
 
+/* On-device Rayleigh-Ritz (the stop decision of the Lanczos iteration taken by an extra CTA of the solver launch; replaces
+ * the 4x4 `eigh` + residual test of nx:239-245): whether this handle uses it, how many eigen-solves since the last counter
+ * reset fell back to the host-driven path, and status / order k / number of checks of the last solve. */
+int macb_device_rr_stats(macb_handle h, int* enabled, int64_t* fallbacks, int* last_status, int* last_k, int* last_checks,
+                         double* last_theta_est_target /* [13]: smallest Ritz value, residual estimate, its target, cycles the
+                                                           Rayleigh-Ritz CTA waited / computed, coefficients published beyond k when
+                                                           it decided, multisection rounds, cycles per stage (6); may be NULL */);
+
 /* cudaDeviceSynchronize on the handle's device. */
 int macb_device_sync(macb_handle h);
 

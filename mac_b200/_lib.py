@@ -80,6 +80,7 @@ def lib():
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_host_build_jds, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int32, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip])
+    _sig(L.macb_device_rr_stats, [H, C.POINTER(C.c_int), _lp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp])
     _sig(L.macb_measure_l2_bandwidth, [C.c_int, C.c_int64, C.c_int, _dp])
     _sig(L.macb_version, [], C.c_char_p)
     _lib = L
@@ -226,6 +227,16 @@ class Handle:
         self._L.macb_counters(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d), ms)
         return {"kernel_launches": a.value, "spmv_launches": b.value, "lanczos_steps": c_.value,
                 "fiedler_solves": d.value, "phase_ms": dict(zip(T_NAMES, list(ms)))}
+
+    def device_rr_stats(self):
+        en, st, k, ch = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        fb = C.c_int64()
+        tet = (C.c_double * 13)()
+        self._L.macb_device_rr_stats(self._h, C.byref(en), C.byref(fb), C.byref(st), C.byref(k), C.byref(ch), tet)
+        return {"enabled": bool(en.value), "fallbacks": fb.value, "last_status": st.value, "last_k": k.value, "last_checks": ch.value,
+                "last_theta": tet[0], "last_est": tet[1], "last_target": tet[2], "cycles_waiting": tet[3], "cycles_computing": tet[4],
+                "lag_steps_at_decision": int(tet[5]), "multisection_rounds": int(tet[6]),
+                "cycles_by_stage": dict(zip(["fetch", "bounds", "warm_bracket", "multisection", "twisted", "rest"], [int(v) for v in tet[7:13]]))}
 
     def reset_counters(self):
         self._L.macb_reset_counters(self._h)

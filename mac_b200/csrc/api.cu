@@ -112,6 +112,15 @@ struct macb_ctx {
     int vec_batch = 5;             // gathers in flight per thread in k_lanczos_vec (3..8, chosen from the slots per thread)
     bool pipe = true;              // k_lanczos_pipe (pipelined recurrence, reduction off the critical path) instead of k_lanczos_vec
     size_t pipe_smem = 0;
+    bool force_host_rr = false;    // this solve only: host-driven path (fallback after a failed device-side decision)
+    bool dev_rr = false;           // Rayleigh-Ritz / stop decision on the device (extra CTA of the k_lanczos_pipe launch)
+    double *d_rr_a = nullptr, *d_rr_b = nullptr, *d_rr_b2 = nullptr, *d_rr_binv = nullptr, *d_rr_s = nullptr, *d_rr_w = nullptr;
+    RrOut* d_rr_out = nullptr;
+    RrOut* h_rr = nullptr;         // pinned
+    RrArgs rr_launch = {};         // filled by enqueue_fiedler_device for the next k_lanczos_pipe launch (enabled = 0 otherwise)
+    int* d_dev_stop = nullptr;
+    double lz_algo_bytes = 0.0;    // bench mode: sum over timed launches of phases x algorithmic bytes at that launch's support
+    int64_t c_dev_fallbacks = 0;   // eigen-solves that fell back from the device-side decision to the host-driven path
     bool sect_joint = false;       // d_sect[1] points into d_sect[0]'s allocation
     double* d_zprev = nullptr;     // z_{j-1} across launches of k_lanczos_pipe
     bool l2_pinned = false;        // this handle holds a reference on the device's persisting-L2 carve-out
@@ -142,6 +151,10 @@ struct macb_ctx {
     unsigned int* d_blockcnt = nullptr;
     SelState* h_sel_state = nullptr;  // pinned
     SelState* d_sel_state2 = nullptr;
+    unsigned int* d_sel2_hist = nullptr;       // two-pass top-k: global 15-bit histogram, state, candidate keys of the chosen bin
+    Sel2State* d_sel2 = nullptr;
+    unsigned long long* d_sel_cand = nullptr;
+    bool topk8 = false;
     double *d_tmp_m2 = nullptr, *d_tmp_m3 = nullptr;
     cudaGraphExec_t sel_graph = nullptr;
 
@@ -291,7 +304,7 @@ void free_all(macb_ctx* c) {
                      c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
                      c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->sect_joint ? nullptr : c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
                      c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec, c->d_sj_chunk_row, c->d_sj_chunk_jd, c->d_sj_jd,
-                     c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0, c->d_zprev};
+                     c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0, c->d_zprev, c->d_rr_a, c->d_rr_b, c->d_rr_b2, c->d_rr_binv, c->d_rr_s, c->d_rr_out, c->d_dev_stop, c->d_rr_w, c->d_sel2_hist, c->d_sel2, c->d_sel_cand};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
@@ -300,6 +313,7 @@ void free_all(macb_ctx* c) {
     if (c->h_sel_state) cudaFreeHost(c->h_sel_state);
     if (c->h_ab) cudaFreeHost(c->h_ab);
     if (c->h_stop) cudaFreeHost(c->h_stop);
+    if (c->h_rr) cudaFreeHost(c->h_rr);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->it0) cudaEventDestroy(c->it0);
@@ -350,7 +364,7 @@ void upload_start(macb_ctx* c, const double* x0_in) {
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-void launch_assemble(macb_ctx* c) {
+void launch_assemble(macb_ctx* c, bool sync = true) {
     PhaseTimer pt(c, MACB_T_ASSEMBLE);
     const int grid = c->grid_rows();
     DISPATCH_W(c->W, k_assemble<WW><<<grid, kBlock, 0, c->stream>>>(c->n, c->d_rp, c->d_eid, c->d_ew, c->d_val,
@@ -365,6 +379,10 @@ void launch_assemble(macb_ctx* c) {
     }
     CK(cudaGetLastError());
     c->c_launches++;
+    c->have_v = false;
+    c->have_g = false;
+    c->have_sel = false;
+    if (!sync) return;   // the caller reads ||L||_inf and the support size with the rest of the iteration's scalars
     CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->lnorm = c->h_sc->lnorm;
@@ -452,8 +470,13 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         void* params[] = {&a, &J};
         void* fn = c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>;
         if (c->jds_vec && c->pipe) {
-            LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, nullptr};
-            void* pparams[] = {&a, &J, &P};
+            LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
+            RrArgs R = c->rr_launch;
+            if (R.enabled) {   // device-side decision: nothing is streamed to, or polled from, the host
+                a.ab_host = nullptr;
+                a.stop = nullptr;
+            }
+            void* pparams[] = {&a, &J, &P, &R};
             void* pf;
             switch (c->vec_batch) {
                 case 3: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 3> : (void*)k_lanczos_pipe<false, 3>; break;
@@ -463,7 +486,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
                 case 8: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 8> : (void*)k_lanczos_pipe<false, 8>; break;
                 default: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 5> : (void*)k_lanczos_pipe<false, 5>; break;
             }
-            CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
+            CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta + (R.enabled ? 1 : 0)), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
             if (c->bench_time_iters) CK(cudaEventRecord(c->lz1, c->stream));
             c->c_launches += 1;
             if (!async) {
@@ -619,7 +642,7 @@ void setup_persist(macb_ctx* c) {
             // graphs are spread over many SMs (the counter barrier of the older engines preferred few)
             int64_t quantum = 4 * kPBlock;
             if (const char* env = getenv("MACB_CTA_QUANTUM")) quantum = std::max(64, atoi(env));
-            c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>((total + quantum - 1) / quantum, c->sm_count));
+            c->p_ncta = (int)std::max<int64_t>(1, std::min<int64_t>((total + quantum - 1) / quantum, c->sm_count - 1));   // one SM stays free for the Rayleigh-Ritz CTA
             rs.assign((size_t)c->p_ncta + 1, n);
             rs[0] = 0;
             int row = 0;
@@ -723,6 +746,20 @@ void setup_persist(macb_ctx* c) {
                 }
                 c->jds_vec = !getenv("MACB_NO_VEC");
                 c->d_zprev = dalloc<double>((size_t)n);
+                if (c->pipe && !getenv("MACB_HOST_RR")) {
+                    const size_t cap2 = (size_t)c->basis_cap + 4;
+                    c->d_rr_a = dalloc<double>(cap2);
+                    c->d_rr_b = dalloc<double>(cap2);
+                    c->d_rr_b2 = dalloc<double>(cap2);
+                    c->d_rr_binv = dalloc<double>(cap2);
+                    c->d_rr_s = dalloc<double>(cap2);
+                    c->d_rr_w = dalloc<double>(4 * cap2);
+                    c->d_rr_out = dalloc<RrOut>(1);
+                    c->d_dev_stop = dalloc<int>(1);
+                    CK(cudaMallocHost(&c->h_rr, sizeof(RrOut)));
+                    CK(cudaMemsetAsync(c->d_dev_stop, 0, sizeof(int), c->stream));
+                    c->dev_rr = true;
+                }
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {
                     // keep the weights the Lanczos kernel streams every step (8 bytes per slot) in the persisting part of L2
@@ -872,7 +909,7 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
     for (int t = 0; t < k; ++t) coef[t] = s[t] / c->h_beta[t];
     CK(cudaMemcpyAsync(c->d_coef, coef.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
     k_ritz<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(),
-                                                        c->persist_v == 5 ? c->d_jrow : nullptr);
+                                                        c->persist_v == 5 ? c->d_jrow : nullptr, nullptr);
     k_center_normalize<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_sc);
     launch_spmv<2>(c, c->d_v, c->d_y);
     k_resid_l1<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_y, c->d_sc, c->ws());
@@ -1075,6 +1112,70 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
     }
 }
 
+// ---- eigen-solve with the stop decision on the device (k_lanczos_pipe + its Rayleigh-Ritz CTA) -------------------------------
+// Everything is enqueued on the handle's stream and NOTHING is read back: start vector -> z_0 = L u_0 -> ONE cooperative launch
+// (solver CTAs + the Rayleigh-Ritz CTA that stops them) -> Ritz vector with the order k and the coefficients the device left
+// -> normalisation -> Rayleigh quotient and the reference's residual (nx:243).  The caller synchronises when IT needs the
+// numbers (macb_fw_run: once per Frank-Wolfe iteration) and then calls finish_fiedler_device.
+bool device_fiedler_available(const macb_ctx* c) { return c->persist && c->persist_v == 5 && c->jds_vec && c->pipe && c->dev_rr; }
+
+void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_warm) {
+    const int n = c->n;
+    const int k_lim = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps, n - 1));
+    const double* src = (use_warm && c->have_prev_v) ? c->d_v : c->d_x0;
+    launch_spmv<0>(c, src, c->d_y);   // z_0 = L u_0 (the shift is applied by the init kernel)
+    k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1], c->d_basis,
+                                                              c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst, c->d_alpha,
+                                                              c->d_beta, k_lim + 2, c->d_rr_out, c->d_dev_stop);
+    CK(cudaGetLastError());
+    RrArgs R;
+    R.alpha = c->d_alpha; R.beta = c->d_beta;
+    R.a = c->d_rr_a; R.b = c->d_rr_b; R.b2 = c->d_rr_b2; R.binv = c->d_rr_binv; R.s = c->d_rr_s;
+    {
+        const size_t cap2 = (size_t)c->basis_cap + 4;
+        R.dp = c->d_rr_w; R.dm = c->d_rr_w + cap2; R.lp = c->d_rr_w + 2 * cap2; R.um = c->d_rr_w + 3 * cap2;
+    }
+    R.coef = c->d_coef; R.out = c->d_rr_out; R.dev_stop = c->d_dev_stop; R.sc = c->d_sc;
+    R.tol = tol; R.n = n; R.k_limit = k_lim; R.check_div = c->check_div; R.enabled = 1;
+    c->rr_launch = R;
+    launch_persist(c, k_lim + 1, true);
+    c->rr_launch.enabled = 0;
+    k_ritz<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->ld, 0, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(), c->d_jrow, c->d_rr_out);
+    k_center_normalize<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->d_v, c->d_sc);
+    launch_spmv<2>(c, c->d_v, c->d_y);
+    k_resid_l1<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->d_v, c->d_y, c->d_sc, c->ws());
+    CK(cudaGetLastError());
+    c->c_launches += 7;
+    c->c_spmv += 2;
+    c->c_solves++;
+    c->have_v = true;
+    c->have_prev_v = true;
+}
+
+// After the stream has been synchronised with h_sc / h_rr copied back: the numbers of the solve.  false = the device-side
+// decision did not produce a pair that passes the reference's residual test (the estimate was optimistic, the cycle ran out
+// of basis, the eigenvector recurrence failed, ...): the caller repeats the solve on the host-driven path.
+bool finish_fiedler_device(macb_ctx* c, double tol, FiedlerResult& out) {
+    const RrOut& r = *c->h_rr;
+    c->lnorm = c->h_sc->lnorm;
+    c->nnz_active = c->h_sc->nnz_active;
+    c->c_steps += r.phases;
+    c->c_spmv += r.phases;
+    if (c->bench_time_iters) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->lz0, c->lz1));
+        c->lz_kernel_ms += ms;
+        c->lz_kernel_phases += r.phases;
+        c->lz_algo_bytes += (double)r.phases * ((double)(c->nnz_active + c->n) * 12.0 + ((double)c->n + 1.0) * 4.0 + 40.0 * (double)c->n);
+    }
+    out.steps = r.phases;
+    if (!(c->lnorm > 0.0) || r.status <= 0 || r.k <= 0) return false;
+    out.lambda2 = c->h_sc->vLv / c->h_sc->vv;
+    out.resid = c->h_sc->res1 / (std::sqrt(c->h_sc->vv) * c->lnorm);
+    out.converged = out.resid < tol;
+    return out.converged;
+}
+
 // Deflated Lanczos on P L(x) P.  Replaces nx:149-253 (see macb200.h).
 int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult& out) {
     if (!c->have_x) throw ArgFail{"macb_fiedler: call macb_set_x first", MACB_ERR_STATE};
@@ -1082,10 +1183,20 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     if (max_steps <= 0) max_steps = 20000;
     PhaseTimer pt(c, MACB_T_FIEDLER);
     ensure_basis(c, max_steps);
-    c->c_solves++;
     const int n = c->n;
     const double sqrtn = std::sqrt((double)n);
     const double lnorm = c->lnorm;
+    if (lnorm > 0.0 && device_fiedler_available(c) && !c->force_host_rr) {
+        // stop decision on the device: enqueue everything, ONE synchronisation, read the numbers
+        enqueue_fiedler_device(c, tol, max_steps, warm != 0);
+        CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_rr, c->d_rr_out, sizeof(RrOut), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (finish_fiedler_device(c, tol, out)) return MACB_OK;
+        c->c_dev_fallbacks++;   // rare: repeat on the host-driven path below (restarts, twisted factorisation, resume)
+        c->c_solves--;
+    }
+    c->c_solves++;
     if (!(lnorm > 0.0)) {  // empty graph: every vector orthogonal to 1 is a null vector
         CK(cudaMemcpyAsync(c->d_v, c->d_x0, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
         out = FiedlerResult{};
@@ -1109,7 +1220,8 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
             c->c_launches++;
             c->c_spmv++;
             k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1],
-                                                                      c->d_basis, c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
+                                                                      c->d_basis, c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst,
+                                                                      c->d_alpha, c->d_beta, 0, nullptr, nullptr);
         } else if (c->persist && c->persist_v == 5 && c->jds_vec) {
             k_lz_vec_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_jrow, c->d_sect[0], c->d_sect[1], c->d_xrec,
                                                                      (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
@@ -1264,12 +1376,21 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
     const int grid = c->grid_for(m);
     k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
     c->c_launches++;
-    if (k > 0) {
+    if (k > 0 && c->topk8) {   // MACB_TOPK8=1: the eight-pass radix select (kept for A/B)
         for (int shift = 56; shift >= 0; shift -= 8) {
             k_sel_hist<<<grid, kBlock, 0, c->stream>>>(m, g, st, shift);
             k_sel_pick<<<1, kBlock, 0, c->stream>>>(st, shift);
         }
         c->c_launches += 16;
+    } else if (k > 0 && m <= kSel2SmallMax) {
+        k_sel2_small<<<1, kSel2Block, kSel2Bins * sizeof(unsigned int), c->stream>>>(m, g, (long long)k, st);
+        c->c_launches += 1;
+    } else if (k > 0) {
+        const int grid2 = (int)std::min<int64_t>(c->sm_count, (m + 4095) / 4096);
+        k_sel2_hist<<<grid2, kSel2Block, kSel2Bins * sizeof(unsigned int), c->stream>>>(m, g, (long long)k, c->d_sel2_hist, c->d_sel2);
+        k_sel2_compact<<<grid, kBlock, 0, c->stream>>>(m, g, c->d_sel2, c->d_sel_cand);
+        k_sel2_refine<<<1, kSel2Block, 0, c->stream>>>(c->d_sel2, c->d_sel_cand, st);
+        c->c_launches += 3;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_sel_state, st, sizeof(SelState), cudaMemcpyDeviceToHost, c->stream));
@@ -1462,6 +1583,14 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         c->d_counter = dalloc<unsigned int>(8);
         c->d_sel_state = dalloc<SelState>(1);
         c->d_blockcnt = dalloc<unsigned int>(c->grid_max + 8);
+        c->d_sel2_hist = dalloc<unsigned int>(kSel2Bins);
+        c->d_sel2 = dalloc<Sel2State>(1);
+        c->d_sel_cand = dalloc<unsigned long long>(m);
+        CK(cudaMemsetAsync(c->d_sel2_hist, 0, kSel2Bins * sizeof(unsigned int), c->stream));
+        CK(cudaMemsetAsync(c->d_sel2, 0, sizeof(Sel2State), c->stream));
+        CK(cudaFuncSetAttribute((const void*)k_sel2_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSel2Bins * sizeof(unsigned int))));
+        CK(cudaFuncSetAttribute((const void*)k_sel2_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSel2Bins * sizeof(unsigned int))));
+        c->topk8 = getenv("MACB_TOPK8") != nullptr;
         CK(cudaMallocHost(&c->h_sc, sizeof(LzScalars)));
         CK(cudaMallocHost(&c->h_sel_state, sizeof(SelState)));
         CK(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(unsigned int), c->stream));
@@ -1714,6 +1843,7 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
             CK(cudaEventElapsedTime(&ms, h->it0, h->it1));
             h->iter_ms.push_back(ms);
         };
+        if (h->n >= 2 && max_iters > 0) ensure_basis(h, fiedler_max_steps > 0 ? fiedler_max_steps : 20000);
         for (; it < max_iters; ++it) {
             if (h->bench_time_iters) {
                 if (h->bench_flush) {
@@ -1722,15 +1852,45 @@ int macb_fw_run(macb_handle h, int64_t k, const double* x_init, int max_iters, d
                 }
                 CK(cudaEventRecord(h->it0, h->stream));
             }
-            launch_assemble(h);  // L(x)                          mac.py:115 -> :74
-            h->have_x = true;
-            FiedlerResult fr;    // f, v                          mac.py:115 -> fiedler.py:9
-            int rc = run_fiedler(h, fiedler_tol, fiedler_max_steps, warm && it > 0, fr);
+            FiedlerResult fr;
+            int rc = MACB_OK;
+            if (h->d_basis && device_fiedler_available(h)) {
+                // The whole iteration is enqueued without a single read-back -- assemble L(x), eigen-solve with the stop
+                // decision on the device, gradient, top-k -- and the host synchronises ONCE to read its scalars.
+                launch_assemble(h, false);  // L(x)                   mac.py:115 -> :74
+                h->have_x = true;
+                {
+                    PhaseTimer pt(h, MACB_T_FIEDLER);
+                    enqueue_fiedler_device(h, fiedler_tol, fiedler_max_steps > 0 ? fiedler_max_steps : 20000, warm && it > 0);
+                }
+                launch_gradient(h);         // g                      mac.py:117-124
+                launch_topk(h, h->d_g, h->d_x, k, h->d_sel, nullptr, true);  // s    frankwolfe.py:58
+                CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(h->h_rr, h->d_rr_out, sizeof(RrOut), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                if (!finish_fiedler_device(h, fiedler_tol, fr)) {
+                    // the device-side decision did not deliver a pair that passes the residual test: host-driven solve
+                    h->c_dev_fallbacks++;
+                    h->c_solves--;
+                    h->force_host_rr = true;
+                    rc = run_fiedler(h, fiedler_tol, fiedler_max_steps, warm && it > 0, fr);
+                    h->force_host_rr = false;
+                    launch_gradient(h);
+                    launch_topk(h, h->d_g, h->d_x, k, h->d_sel, nullptr, true);
+                    CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+                    CK(cudaStreamSynchronize(h->stream));
+                }
+            } else {
+                launch_assemble(h);  // L(x)                          mac.py:115 -> :74
+                h->have_x = true;
+                //                      f, v                          mac.py:115 -> fiedler.py:9
+                rc = run_fiedler(h, fiedler_tol, fiedler_max_steps, warm && it > 0, fr);
+                launch_gradient(h);  // g                             mac.py:117-124
+                launch_topk(h, h->d_g, h->d_x, k, h->d_sel, nullptr, true);  // s    frankwolfe.py:58
+                CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
             if (rc == MACB_NOT_CONVERGED) status = MACB_NOT_CONVERGED;
-            launch_gradient(h);  // g                             mac.py:117-124
-            launch_topk(h, h->d_g, h->d_x, k, h->d_sel, nullptr, true);  // s    frankwolfe.py:58
-            CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
             if (topk_fixup(h, h->d_g, h->d_x, k, h->d_sel)) {   // ties at the k-th value: lowest index first
                 CK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
                 CK(cudaStreamSynchronize(h->stream));
@@ -1794,6 +1954,8 @@ int macb_reset_counters(macb_handle h) {
     h->c_launches = h->c_spmv = h->c_steps = h->c_solves = 0;
     h->lz_kernel_ms = 0.0;
     h->lz_kernel_phases = 0;
+    h->lz_algo_bytes = 0.0;
+    h->c_dev_fallbacks = 0;
     for (int i = 0; i < MACB_T_COUNT; ++i) h->phase_ms[i] = 0.0;
     return MACB_OK;
 }
@@ -1856,7 +2018,11 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
     // one Lanczos phase = one SpMV ((nnz + n) * 12 + 4 (n + 1) + 16 n) plus what the engine writes per node:
     // the 32-byte state sector and the 8-byte basis entry (sector engines), or the new vector entry, the basis entry
     // and the poison word (k_lanczos_vec)
-    if (algo_bytes_per_phase) {
+    if (algo_bytes_per_phase && h->lz_algo_bytes > 0.0 && h->lz_kernel_phases > 0) {
+        // device-side decision: bytes follow the ACTIVE slots of every timed launch (zero-weight slots issue no gather and no
+        // weight load): sum over launches of phases x [(nnz_active + n) 12 + 4 (n + 1) + 16 n + 24 n] / phases
+        *algo_bytes_per_phase = h->lz_algo_bytes / (double)h->lz_kernel_phases;
+    } else if (algo_bytes_per_phase) {
         const double spmv = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n;
         const bool vec = h->persist && h->persist_v == 5 && h->jds_vec;
         *algo_bytes_per_phase = spmv + (vec ? 24.0 : 40.0) * (double)h->n;
@@ -1913,6 +2079,27 @@ int macb_measure_l2_bandwidth(int device, int64_t bytes, int reps, double* gbs) 
         cudaGetLastError();
         return MACB_ERR_CUDA;
     }
+}
+
+int macb_device_rr_stats(macb_handle h, int* enabled, int64_t* fallbacks, int* last_status, int* last_k, int* last_checks,
+                         double* last_theta_est_target /*[3], may be NULL*/) {
+    if (!h) return MACB_ERR_ARG;
+    if (enabled) *enabled = device_fiedler_available(h) ? 1 : 0;
+    if (fallbacks) *fallbacks = h->c_dev_fallbacks;
+    if (last_status) *last_status = h->h_rr ? h->h_rr->status : 0;
+    if (last_k) *last_k = h->h_rr ? h->h_rr->k : 0;
+    if (last_checks) *last_checks = h->h_rr ? h->h_rr->checks : 0;
+    if (last_theta_est_target && h->h_rr) {
+        last_theta_est_target[0] = h->h_rr->theta;
+        last_theta_est_target[1] = h->h_rr->est;
+        last_theta_est_target[2] = h->h_rr->target;
+        last_theta_est_target[3] = (double)h->h_rr->cyc_wait;
+        last_theta_est_target[4] = (double)h->h_rr->cyc_compute;
+        last_theta_est_target[5] = (double)h->h_rr->lag;
+        last_theta_est_target[6] = (double)h->h_rr->rounds;
+        for (int i = 0; i < 6; ++i) last_theta_est_target[7 + i] = (double)h->h_rr->cyc_stage[i];
+    }
+    return MACB_OK;
 }
 
 int macb_device_sync(macb_handle h) {

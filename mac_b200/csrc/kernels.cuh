@@ -1698,6 +1698,39 @@ __device__ __forceinline__ double lz_row_sum(const double* __restrict__ prod, co
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+struct RrOut {
+    int status;      // 0 running; 1 estimate below target; 2 cycle exhausted (k_limit); 3 invariant subspace (breakdown);
+                     // -1 non-finite coefficient; -2 eigenvector recurrence failed; -3 timed out waiting for coefficients
+    int k;           // order of the T_k the decision (and coef) refers to
+    int checks;
+    int phases;      // phases the solver completed (written by solver CTA 0 at exit)
+    double theta, est, target;
+    long long cyc_wait, cyc_compute;   // diagnostics: cycles spent waiting for coefficients / computing
+    int lag;                           // coefficients the solver had published beyond `k` when the decision fell
+    int rounds;                        // multisection rounds, all checks
+    long long cyc_stage[6];            // fetch, bounds, warm bracket, multisection, twisted factorisation + sweeps, rest
+};
+
+struct RrArgs {
+    const double* alpha;   // [cap + 1] published by the solver, NaN = not yet
+    const double* beta;    // [cap + 2]
+    double* a;             // private copies / derived arrays, [cap + 2] each
+    double* b;
+    double* b2;
+    double* binv;
+    double* s;
+    double* dp;            // twisted factorisation: forward / backward pivots and multipliers, [cap + 2] each
+    double* dm;
+    double* lp;
+    double* um;
+    double* coef;          // out [cap + 1]: s_t / beta_t
+    RrOut* out;
+    int* dev_stop;
+    const LzScalars* sc;   // sc->lnorm
+    double tol;
+    int n, k_limit, check_div, enabled;
+};
+
 struct LzPipeArgs {
     const LzScalars* sc;   // sc->shift = trace(L)/n (k_assemble)
     double* zprev;         // [n] z_{j-1} of the CTA's rows across launches (engine numbering)
@@ -1711,9 +1744,21 @@ struct LzPipeArgs {
 __global__ void __launch_bounds__(kBlock) k_lz_pipe_init(int n, const double* __restrict__ src, const double* __restrict__ lsrc,
                                                          const int* __restrict__ perm, const LzScalars* sc, double* __restrict__ z0,
                                                          double* __restrict__ z1, double* __restrict__ basis0, double* __restrict__ xrec,
-                                                         int64_t nxrec, LzPersistState* st) {
+                                                         int64_t nxrec, LzPersistState* st, double* __restrict__ alpha,
+                                                         double* __restrict__ beta, int ncoef, RrOut* rr_out, int* dev_stop) {
     const double nan1 = __longlong_as_double(0x7ff8000000000001ll);
     const double sigma = sc->shift;
+    // coefficients not yet produced read as NaN (the Rayleigh-Ritz CTA waits for every entry on its own)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncoef; i += gridDim.x * blockDim.x) {
+        alpha[i] = nan1;
+        beta[i] = nan1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && rr_out) {
+        rr_out->status = 0; rr_out->k = 0; rr_out->checks = 0; rr_out->phases = 0;
+        rr_out->theta = 0.0; rr_out->est = 0.0; rr_out->target = 0.0;
+        rr_out->cyc_wait = 0; rr_out->cyc_compute = 0; rr_out->lag = 0; rr_out->rounds = 0;
+        *dev_stop = 0;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = perm[i];
         const double u = src[c];
@@ -1732,6 +1777,562 @@ __global__ void __launch_bounds__(kBlock) k_lz_pipe_init(int n, const double* __
     }
 }
 
+// ---- On-device Rayleigh-Ritz: the stop decision of the Lanczos iteration (replaces the 4x4 `eigh` + residual test of the
+// reference's loop, nx:239-245, and the host thread that used to poll the coefficients over PCIe) ---------------------------------
+// One extra CTA of the cooperative Lanczos launch (block index == number of solver CTAs).  It follows the coefficients
+// (alpha_j, beta_j) that solver CTA 0 publishes in device memory, and at check points that depend on the coefficient sequence
+// only (so a solve is a pure function of its input, whatever the timing) computes the smallest eigenpair (theta, s) of T_k:
+//   theta   1024-way multisection on the Sturm count (every thread one shift; the bracket shrinks 1025x per round), started
+//           from a geometric bracket below the previous theta (Ritz values decrease monotonically with k);
+//   s       forward pivot recurrence (stable for the smallest eigenvalue: T_j - theta I is positive semi-definite for every
+//           leading block), one thread;
+//   est     |beta_k s_{k-1}| = 2-norm of the residual of the Ritz pair; stop when 0.88 est sqrt(n) < tol ||L||_inf (the
+//           reference's test ||r||_1 / ||L||_inf < tol with ||r||_1 ~ 0.80 sqrt(n) ||r||_2 for a Gaussian-like residual and
+//           10 % margin; the TRUE residual is tested after the kernel in any case).
+// On the decision it raises a device-resident flag that solver CTA 0 reads once per phase, and leaves k, theta and the Ritz
+// coefficients s_t / beta_t for k_ritz.  The host sees nothing of this until it reads the result of the whole FW iteration.
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// block-wide (1024 threads) max of a value; result on every thread
+__device__ __forceinline__ double rr_block_max(double v, double* red /*[32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, red[w]);
+    return r;
+}
+
+__device__ __forceinline__ double rr_block_sum(double v, double* red /*[32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += red[w];
+    return r;
+}
+
+// true iff T_k has an eigenvalue below x (Sturm sequence, early exit on the first negative pivot)
+// 1/x to about one ulp: hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps.  An IEEE double division is a ~40-instruction
+// sequence with ~250 cycles of latency on this chip, and the Sturm recurrence below is one long chain of them: the check of a
+// T_190 took 180 us and the solver overshot its stopping point by 60 % (measured); the recurrence is backward stable with
+// respect to such last-bit errors (they are relative perturbations of the matrix entries of the same size).
+template <int NEWTON = 2>
+__device__ __forceinline__ double rr_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < NEWTON; ++it) {
+        const double e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+    }
+    return r;
+}
+
+// The two pivot chains of the twisted factorisation of T_k - theta I (one thread each) and the two product sweeps.  Separate
+// functions with __restrict__ arrays: written inline on aliasing pointers, every load waits for the previous row's stores.
+// NEWTON = 1 (reciprocals to ~1e-12) for the checks, which need the estimate to 10 %; 2 for the accepted pair.
+template <int NEWTON>
+__device__ __forceinline__ void rr_pivots_down(const double* __restrict__ a, const double* __restrict__ b, int k, double theta, double tiny,
+                                               double* __restrict__ dp, double* __restrict__ lp) {
+    double d = a[0] - theta;
+    for (int i = 0; i + 1 < k; ++i) {
+        if (fabs(d) < tiny) d = (d < 0.0 ? -tiny : tiny);
+        dp[i] = d;
+        const double bn = b[i + 1];
+        const double l = bn * rr_rcp<NEWTON>(d);
+        lp[i] = l;
+        d = fma(-l, bn, a[i + 1] - theta);
+    }
+    dp[k - 1] = d;
+}
+template <int NEWTON>
+__device__ __forceinline__ void rr_pivots_up(const double* __restrict__ a, const double* __restrict__ b, int k, double theta, double tiny,
+                                             double* __restrict__ dm, double* __restrict__ um) {
+    double d = a[k - 1] - theta;
+    for (int i = k - 2; i >= 0; --i) {
+        if (fabs(d) < tiny) d = (d < 0.0 ? -tiny : tiny);
+        dm[i + 1] = d;
+        const double bn = b[i + 1];
+        const double u = bn * rr_rcp<NEWTON>(d);
+        um[i] = u;
+        d = fma(-u, bn, a[i] - theta);
+    }
+    dm[0] = d;
+}
+// Eigenvector of T_k for theta without a single division: the three-term recurrence run from the top (f) and from the bottom
+// (g), one thread each, joined at the index r of the largest |f| -- the vector of the twisted factorisation at that r, obtained
+// through the minors instead of the pivots: ~25 cycles per row instead of ~100 (a pivot costs a reciprocal).  The recurrence from
+// the top is accurate until the entries start to decay (the decaying solution is the recessive one), which is after their
+// maximum; the one from the bottom is accurate all the way up to there (it follows the growing solution).
+__device__ __forceinline__ void rr_three_term_down(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ binv,
+                                                   int k, double theta, double* __restrict__ f) {
+    double f0 = 1.0, f1 = (k > 1) ? -(a[0] - theta) * binv[1] : 0.0;
+    f[0] = f0;
+    if (k > 1) f[1] = f1;
+    for (int i = 1; i + 1 < k; ++i) {
+        const double fn = -fma(a[i] - theta, f1, b[i] * f0) * binv[i + 1];
+        f[i + 1] = fn;
+        f0 = f1;
+        f1 = fn;
+    }
+}
+__device__ __forceinline__ void rr_three_term_up(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ binv,
+                                                 int k, double theta, double* __restrict__ g) {
+    double g0 = 1.0, g1 = (k > 1) ? -(a[k - 1] - theta) * binv[k - 1] : 0.0;   // g0 = g_{k-1}, g1 = g_{k-2}
+    g[k - 1] = g0;
+    if (k > 1) g[k - 2] = g1;
+    for (int i = k - 2; i >= 1; --i) {
+        const double gn = -fma(a[i] - theta, g1, b[i + 1] * g0) * binv[i];
+        g[i - 1] = gn;
+        g0 = g1;
+        g1 = gn;
+        if (fabs(gn) > 1e200) {   // grows towards the top: rescale what has been written so far (rare)
+            for (int t = i - 1; t < k; ++t) g[t] *= 1e-200;
+            g0 *= 1e-200;
+            g1 *= 1e-200;
+        }
+    }
+}
+
+__device__ __forceinline__ bool rr_sweep_up(const double* __restrict__ lp, int r, double* __restrict__ sv) {
+    double v = 1.0;
+    sv[r] = 1.0;
+    for (int i = r - 1; i >= 0; --i) {
+        v = -lp[i] * v;
+        sv[i] = v;
+    }
+    return fabs(v) < 1e140 || r == 0;   // (the entries decay away from r; a runaway product shows in the last one)
+}
+__device__ __forceinline__ bool rr_sweep_down(const double* __restrict__ um, int r, int k, double* __restrict__ sv) {
+    double v = 1.0;
+    for (int i = r; i + 1 < k; ++i) {
+        v = -um[i] * v;
+        sv[i + 1] = v;
+    }
+    return fabs(v) < 1e140;
+}
+
+// True iff T_k has an eigenvalue below x: a sign change in the sequence of leading principal minors p_i(x) of T - x I,
+//     p_0 = 1,  p_1 = a_0 - x,  p_{i+1} = (a_i - x) p_i - b_i^2 p_{i-1}
+// (the pivot of the LDL^T factorisation is q_i = p_{i+1} / p_i; a zero minor counts as a negative pivot).  Division-free: two
+// dependent fused multiply-adds per row, ~20 cycles, where the pivot form q_i = (a_i - x) - b_i^2 / q_{i-1} is a chain of
+// double-precision divisions (~250 cycles each as an IEEE division, ~100 with a hardware reciprocal seed and two Newton steps):
+// with the pivot form a check of T_190 took 115 - 180 us and the solver overshot its stopping point by 40 - 60 % (measured).
+// The minors are rescaled every fourth row; the shifts this is used for only have to locate theta to ~1e-7 (the accepted
+// pair is polished by a Rayleigh quotient + a second twisted factorisation).  a, b2 are written by this CTA during the same
+// launch: plain pointers -- no __restrict__/const, which would let the compiler use the non-coherent read-only path.
+__device__ __forceinline__ bool rr_eig_below(double* a, double* b2, int k, double x, double pivmin) {
+    (void)pivmin;
+    double p0 = 1.0, p1 = a[0] - x;
+    if (!(p1 > 0.0)) return true;
+    for (int i = 1; i < k; ++i) {
+        const double pn = fma(a[i] - x, p1, -b2[i] * p0);
+        if (!(pn > 0.0) != !(p1 > 0.0) || pn == 0.0) return true;   // (p1 > 0 is an invariant: we leave at the first change)
+        p0 = p1;
+        p1 = pn;
+        if ((i & 3) == 0) {
+            const double m = fabs(p1);
+            if (m > 1e100) {
+                p0 *= 1e-100;
+                p1 *= 1e-100;
+            } else if (m < 1e-100) {
+                p0 *= 1e100;
+                p1 *= 1e100;
+            }
+        }
+    }
+    return false;
+}
+
+// The same count with T_k in SHARED memory (32-bit shared addresses of a[] and b2[], both 16-byte aligned): four rows per trip,
+// their entries fetched with two 16-byte loads per array one trip ahead of their use, so that the chain is the two fused
+// multiply-adds per row and nothing else (~20 cycles per row instead of ~70 with generic loads inside the chain, measured as
+// 13 000 cycles per round on T_190).  Sign changes are collected from the sign bits of consecutive minors (integer pipe); the
+// trip is left at its end, the minors are rescaled there.
+__device__ __forceinline__ void rr_lds4(unsigned int addr, double (&v)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(addr + 16u));
+}
+__device__ __forceinline__ bool rr_eig_below_smem(unsigned int a_addr, unsigned int b2_addr, int k, double x) {
+    // rows are padded to a multiple of four by the caller: a = +huge, b2 = 0 beyond k keep the sign of the minors
+    double av[4], bv[4], an[4], bn[4];
+    rr_lds4(a_addr, av);
+    rr_lds4(b2_addr, bv);
+    double p0 = 1.0, p1 = av[0] - x;
+    int flip = __double2hiint(p1);                  // sign bit set <=> p_1 < 0
+    if (p1 == 0.0) return true;
+    {   // rows 1..3 of the first trip
+        rr_lds4(a_addr + 32u, an);
+        rr_lds4(b2_addr + 32u, bn);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            const double pn = fma(av[j] - x, p1, -bv[j] * p0);
+            flip |= __double2hiint(pn) ^ __double2hiint(p1);
+            p0 = p1;
+            p1 = pn;
+        }
+    }
+    if (flip < 0) return true;
+    for (int i = 4; i < k; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { av[j] = an[j]; bv[j] = bn[j]; }
+        rr_lds4(a_addr + 8u * (unsigned int)(i + 4), an);     // (the arrays are padded by four more entries)
+        rr_lds4(b2_addr + 8u * (unsigned int)(i + 4), bn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double pn = fma(av[j] - x, p1, -bv[j] * p0);
+            flip |= __double2hiint(pn) ^ __double2hiint(p1);
+            p0 = p1;
+            p1 = pn;
+        }
+        if (flip < 0 || !(fabs(p1) < 1e300)) return true;   // (overflow / NaN only after a zero minor: counts as a change)
+        const double m = fabs(p1);
+        if (m > 1e100) {
+            p0 *= 1e-100;
+            p1 *= 1e-100;
+        } else if (m < 1e-100) {
+            p0 *= 1e100;
+            p1 *= 1e100;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ int rr_next_check(int k, int div) { return k + max(div >= 24 ? 4 : 16, (k / div) & ~3); }
+
+__device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_doubles) {
+    __shared__ double red[32];
+    // T_k's diagonal and squared off-diagonal for the Sturm counts: in this CTA's (otherwise unused) dynamic shared memory
+    // while they fit, in the private global arrays beyond that
+    // (every sequential recurrence below is a chain of dependent loads otherwise: an L1 miss to L2 costs 700+ cycles while the
+    // solver CTAs are gathering -- 78 us per check with the arrays in global memory, measured)
+    const int cap_s = (smem_doubles / 8) & ~3;   // multiple of 4: every array stays 32-byte aligned
+    double* const a_s = smem;
+    double* const b2_s = smem + cap_s;
+    double* const b_s = smem + 2 * cap_s;
+    double* const binv_s = smem + 3 * cap_s;
+    double* const w_s = smem + 4 * cap_s;   // f (top-down), g (bottom-up), s
+    __shared__ int s_fail, s_kbreak, s_vec_ok, s_vec_ok2, s_kr;
+    __shared__ double a_pad_save[8], b2_pad_save[8];
+    __shared__ double red4[128];
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const double lnorm = R.sc->lnorm, sqrtn = sqrt((double)R.n);
+    const double brk = fmax(1e-12 * lnorm, 0.25 * R.tol * lnorm / sqrtn);
+    const double target = R.tol * lnorm / (0.88 * sqrtn);
+    const double eps = 2.220446049250313e-16, dmin = 2.2250738585072014e-308;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    int k_seen = 0, k_next = min(16, R.k_limit), checks = 0, k_prev = 0;
+    double theta_prev = inf, theta_delta = -1.0, est_prev = 0.0;
+    if (tid == 0) {
+        s_fail = 0;
+        s_kbreak = 1 << 30;
+    }
+    const long long t_begin = clock64();
+    __syncthreads();
+    int status = 0, k = 0;
+    long long cyc_wait = 0, cyc_stage[6] = {0, 0, 0, 0, 0, 0};
+    double gl = inf, gu = -inf, amin = inf, bmax = 0.0;   // running bounds of T_k
+    int k_bounds = 0;
+    int rounds = 0;
+    double theta = 0.0, est = inf, s_inv = 0.0;
+    bool exhausted = false, s_vok = false;
+    while (true) {
+        const int need = min(k_next, R.k_limit);
+        // ---- new coefficients.  ONE thread waits for the newest entry, slowly (a thousand threads polling the two lines solver
+        // CTA 0 writes every phase slow that CTA down, and with it the whole grid: 31 us per step instead of 7.5, measured);
+        // then every entry is waited for on its own: the solver publishes them with plain stores, nothing orders them
+        const long long tw0 = clock64();
+        if (tid == 0) {
+            unsigned int spin = 0;
+            while (true) {
+                const double be = ld_relaxed_f64(R.beta + need);
+                if (be == be) break;
+                __nanosleep(1000);
+                if ((++spin & 255u) == 0 && clock64() - t_begin > 6000000000ll) {   // ~3 s: the solver is gone
+                    s_fail = 3;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        cyc_wait += clock64() - tw0;
+        long long ts = clock64();
+#define RR_STAGE(i) do { const long long tn_ = clock64(); cyc_stage[i] += tn_ - ts; ts = tn_; } while (0)
+        for (int j = k_seen + tid; j <= need; j += nt) {
+            double al, be;
+            unsigned int spin = 0;
+            while (true) {
+                al = ld_relaxed_f64(R.alpha + j);
+                be = ld_relaxed_f64(R.beta + j);
+                if (al == al && be == be) break;
+                __nanosleep(200);
+                if ((++spin & 1023u) == 0 && clock64() - t_begin > 6000000000ll) {   // ~3 s: the solver is gone
+                    atomicExch(&s_fail, 3);
+                    al = be = 0.0;
+                    break;
+                }
+                if (*(volatile int*)&s_fail) break;
+            }
+            if (!(fabs(al) < inf) || !(fabs(be) < inf)) atomicMax(&s_fail, 1);
+            R.a[j] = al;
+            R.b[j] = be;
+            R.b2[j] = be * be;
+            if (j < cap_s) {
+                a_s[j] = al;
+                b2_s[j] = be * be;
+                b_s[j] = be;
+                binv_s[j] = (be != 0.0) ? 1.0 / be : 0.0;
+            }
+            R.binv[j] = (be != 0.0) ? 1.0 / be : 0.0;
+            if (j >= 1 && !(be > brk)) atomicMin(&s_kbreak, j);   // breakdown: span(u_0..u_{j-1}) is invariant, T_j is exact
+        }
+        __syncthreads();
+        if (s_fail) {
+            status = (s_fail == 3) ? -3 : -1;
+            break;
+        }
+        k_seen = max(k_seen, need + 1);
+        const bool invariant = s_kbreak <= need;
+        k = invariant ? s_kbreak : need;
+        if (k == 0) {
+            status = -1;
+            break;
+        }
+        ++checks;
+        RR_STAGE(0);
+        // ---- bounds: Gershgorin, smallest diagonal entry, largest squared off-diagonal -- running values, only the rows that
+        // are new (or whose lower neighbour is) are looked at; a row's older, smaller radius stays in the min / max harmlessly
+        {
+            double v0 = inf, v1 = -inf, v2 = inf, v3 = 0.0;
+            for (int i = max(k_bounds - 1, 0) + tid; i < k; i += nt) {
+                // (shared copies while they reach: a dependent global load costs ~2 500 cycles under the solver's traffic)
+                const bool sm_ok = i + 1 < cap_s;
+                const double ai = sm_ok ? a_s[i] : ld_relaxed_f64(R.a + i);
+                const double bl = (i > 0) ? fabs(sm_ok ? b_s[i] : ld_relaxed_f64(R.b + i)) : 0.0;
+                const double bu = (i + 1 < k) ? fabs(sm_ok ? b_s[i + 1] : ld_relaxed_f64(R.b + i + 1)) : 0.0;
+                v0 = fmin(v0, ai - (bl + bu));
+                v1 = fmax(v1, ai + (bl + bu));
+                v2 = fmin(v2, ai);
+                if (i > 0) v3 = fmax(v3, bl * bl);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 = fmin(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                v1 = fmax(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                v2 = fmin(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                v3 = fmax(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+            }
+            __syncthreads();
+            if ((tid & 31) == 0) {
+                red4[tid >> 5] = v0; red4[32 + (tid >> 5)] = v1; red4[64 + (tid >> 5)] = v2; red4[96 + (tid >> 5)] = v3;
+            }
+            __syncthreads();
+            for (int w = 0; w < (nt >> 5); ++w) {
+                gl = fmin(gl, red4[w]); gu = fmax(gu, red4[32 + w]); amin = fmin(amin, red4[64 + w]); bmax = fmax(bmax, red4[96 + w]);
+            }
+            k_bounds = k;
+        }
+        const double pivmin = fmax(dmin, dmin * bmax) * 4.0;
+        const double tnorm = fmax(fabs(gl), fabs(gu));
+        const bool in_s = k + 9 <= cap_s;
+        if (in_s && tid < 8) {   // padding rows for the four-row trips of the Sturm count: they keep the sign of the minors
+            a_pad_save[tid] = a_s[k + tid];
+            b2_pad_save[tid] = b2_s[k + tid];
+        }
+        __syncthreads();
+        if (in_s && tid < 8) {
+            a_s[k + tid] = 1e30;
+            b2_s[k + tid] = 0.0;
+        }
+        __syncthreads();
+        const unsigned int a_sh = (unsigned int)__cvta_generic_to_shared(a_s), b2_sh = (unsigned int)__cvta_generic_to_shared(b2_s);
+        double* const pa = in_s ? a_s : R.a;
+        double* const pb2 = in_s ? b2_s : R.b2;
+        double* const pb = in_s ? b_s : R.b;
+        double* const pbinv = in_s ? binv_s : R.binv;
+        double* const pdp = in_s ? w_s : R.dp;
+        double* const pdm = in_s ? w_s + cap_s : R.dm;
+        double* const ps = in_s ? w_s + 2 * cap_s : R.s;
+        double lo = gl - 2.0 * eps * tnorm * k - 2.0 * pivmin;
+        double hi = fmin(gu + 2.0 * eps * tnorm * k + 2.0 * pivmin, amin + 4.0 * eps * tnorm);
+        RR_STAGE(1);
+        // Once two consecutive checks agree on theta to 1e-8 it is no longer searched for: the eigenvector recurrences below
+        // tolerate that error (the tail of the vector moves by (k - i0) d(theta) / gap), and an accepted pair is polished by
+        // its Rayleigh quotient.  Ritz values only decrease with k, by less every check.
+        const bool theta_frozen = theta_prev < inf && theta_delta >= 0.0 && theta_delta < 2e-8 * fabs(theta_prev) && !invariant;
+        if (k == 1) {
+            theta = in_s ? a_s[0] : R.a[0];
+        } else if (theta_frozen) {
+            theta = theta_prev;
+        } else {
+            // ---- warm bracket: probes h, h - d, h - 4 d, h - 16 d, ... below the previous theta
+            if (theta_prev < inf && !invariant) {
+                const double h = theta_prev + 8.0 * eps * tnorm;
+                double d = (theta_delta > 0.0) ? theta_delta : 1e-6 * fmax(fabs(h), 1e-300);
+                d = fmax(d, 16.0 * eps * tnorm);
+                bool neg = false;
+                double x = h;
+                if (tid < 64) {
+                    if (tid > 0) x = h - d * exp2(2.0 * (double)(tid - 1));
+                    if (x > lo && x < hi) neg = in_s ? rr_eig_below_smem(a_sh, b2_sh, k, x) : rr_eig_below(pa, pb2, k, x, pivmin);
+                    else if (x >= hi) neg = true;    // hi is an upper bound of the eigenvalue
+                }
+                const int cnt = __syncthreads_count(neg);   // probes 0 .. cnt-1 lie above the eigenvalue (monotone)
+                if (cnt > 0) {
+                    const double xh = (cnt - 1 == 0) ? h : h - d * exp2(2.0 * (double)(cnt - 2));
+                    const double xl = (cnt >= 64) ? lo : h - d * exp2(2.0 * (double)(cnt - 1));
+                    hi = fmin(hi, xh);
+                    lo = fmax(lo, xl);
+                }
+            }
+            // ---- multisection: kRrProbes interior shifts per round (more would be bound by the SM's 64 FP64 lanes, not by the
+            // latency of the recurrence), down to a relative width of 1e-9: the decision needs the residual estimate to ~10 %,
+            // and the tail of the eigenvector moves by (k - i0) d(theta) / gap -- 1e-7 in theta would do
+            constexpr int kRrProbes = 256;
+            RR_STAGE(2);
+            for (int round = 0; round < 40; ++round) {
+                ++rounds;
+                const double width = hi - lo;
+                if (!(width > 1e-9 * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
+                bool neg = false;
+                if (tid < kRrProbes) {
+                    const double x = lo + width * ((double)(tid + 1) / (double)(kRrProbes + 1));
+                    const bool inside = x > lo && x < hi;
+                    neg = inside ? (in_s ? rr_eig_below_smem(a_sh, b2_sh, k, x) : rr_eig_below(pa, pb2, k, x, pivmin)) : (x >= hi);
+                }
+                const int nonneg = kRrProbes - __syncthreads_count(neg);   // shifts 0 .. nonneg-1 lie below (or at) the eigenvalue
+                const double nlo = (nonneg == 0) ? lo : lo + width * ((double)nonneg / (double)(kRrProbes + 1));
+                const double nhi = (nonneg == kRrProbes) ? hi : lo + width * ((double)(nonneg + 1) / (double)(kRrProbes + 1));
+                const bool stuck = !(nhi - nlo < width);
+                lo = fmax(lo, nlo);
+                hi = fmin(hi, nhi);
+                if (stuck) break;
+            }
+            theta = 0.5 * (lo + hi);
+            RR_STAGE(3);
+        }
+        __syncthreads();
+        if (in_s && tid < 8) {
+            a_s[k + tid] = a_pad_save[tid];
+            b2_s[k + tid] = b2_pad_save[tid];
+        }
+        __syncthreads();
+        for (int polish = 0; polish < 2; ++polish) {
+        // ---- eigenvector of T_k for theta: three-term recurrences from both ends (two threads, side by side), joined at the
+        // index r of the largest entry of the one from the top.  (A recurrence from the top alone cannot resolve the tail of a
+        // converged pair, and est = |beta_k s_{k-1}| needs exactly that tail -- measured: the estimate stalled at 1e-3 of a pair
+        // whose true residual had long passed 1e-9.)
+        if (tid == 0) rr_three_term_down(pa, pb, pbinv, k, theta, pdp);
+        else if (tid == 32) rr_three_term_up(pa, pb, pbinv, k, theta, pdm);
+        __syncthreads();
+        {   // r = argmax |f_i| (ties -> smallest index)
+            double best = -1.0;
+            int bi = 0;
+            for (int i = tid; i < k; i += nt) {
+                const double v = fabs(pdp[i]);
+                if (v > best) {
+                    best = v;
+                    bi = i;
+                }
+            }
+            const double bmaxv = rr_block_max(best, red);
+            if (tid == 0) s_kr = 1 << 30;
+            __syncthreads();
+            if (best == bmaxv) atomicMin(&s_kr, bi);
+            __syncthreads();
+        }
+        const int r_tw = s_kr;
+        const double fr = pdp[r_tw], gr = pdm[r_tw];
+        bool vec_ok = fabs(fr) > 0.0 && fabs(fr) < inf && fabs(gr) > 0.0 && fabs(gr) < inf;
+        const double gscale = vec_ok ? fr / gr : 0.0;
+        double ssq = 0.0;
+        for (int i = tid; i < k; i += nt) {
+            const double v = (i <= r_tw) ? pdp[i] : gscale * pdm[i];
+            ps[i] = v;
+            ssq = fma(v, v, ssq);
+        }
+        ssq = rr_block_sum(ssq, red);
+        vec_ok = vec_ok && ssq > 0.0 && ssq < inf;
+        const double inv = vec_ok ? 1.0 / sqrt(ssq) : 0.0;
+        const double s_last = vec_ok ? ((k - 1 <= r_tw) ? pdp[k - 1] : gscale * pdm[k - 1]) : 0.0;
+        RR_STAGE(4);
+        est = vec_ok ? fabs(pb[k]) * fabs(s_last) * inv : inf;
+        exhausted = invariant || need >= R.k_limit;
+        s_inv = inv;
+        s_vok = vec_ok;
+        if (!(est < target || exhausted) || !vec_ok || polish == 1 || k == 1) break;
+        // accepted on an approximate theta: polish it with the Rayleigh quotient of s (error ~ (d theta)^2 / gap) and redo the
+        // twisted factorisation, so that the Ritz coefficients handed to k_ritz are those of an accurate eigenpair of T_k
+        {
+            double num = 0.0;
+            for (int i = tid; i < k; i += nt) {
+                double t = pa[i] * ps[i];
+                if (i > 0) t = fma(pb[i], ps[i - 1], t);
+                if (i + 1 < k) t = fma(pb[i + 1], ps[i + 1], t);
+                num = fma(ps[i], t, num);
+            }
+            num = rr_block_sum(num, red);
+            theta = num * inv * inv;
+        }
+        }   // polish
+        {
+        const bool vec_ok = s_vok;
+        const double inv = s_inv;
+        if (est < target || exhausted) {
+            status = (est < target) ? 1 : (!vec_ok ? -2 : (invariant ? 3 : 2));
+            for (int t = tid; t < k; t += nt) R.coef[t] = vec_ok ? ps[t] * inv * R.binv[t] : 0.0;
+            break;
+        }
+        }
+        RR_STAGE(5);
+        // ---- next check point: a function of the coefficients only (same rule as the host used: half-way to the step at
+        // which the geometric decay of the estimate is predicted to cross the target, never closer than 4 steps)
+        int nk = rr_next_check(need, R.check_div);
+        if (est_prev > 0.0 && est > target && est < est_prev && k > k_prev) {
+            const double slope = (log(est) - log(est_prev)) / (double)(k - k_prev);
+            const double pred = (log(target) - log(est)) / slope;
+            const double cap = fmax(16.0, 0.25 * (double)k);
+            nk = need + (int)fmax(4.0, fmin(0.5 * pred, cap));
+        }
+        if (theta_prev < inf) theta_delta = 2.0 * fabs(theta_prev - theta);
+        theta_prev = theta;
+        k_prev = k;
+        est_prev = est;
+        k_next = nk;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        R.out->status = status;
+        R.out->k = k;
+        R.out->checks = checks;
+        R.out->theta = theta;
+        R.out->est = est;
+        R.out->target = target;
+        R.out->cyc_wait = cyc_wait;
+        R.out->cyc_compute = (clock64() - t_begin) - cyc_wait;
+        int lag = 0;
+        while (k + 1 + lag <= R.k_limit && lag < 4096) {
+            const double be = ld_relaxed_f64(R.beta + k + 1 + lag);
+            if (be != be) break;
+            ++lag;
+        }
+        R.out->lag = lag;
+        R.out->rounds = rounds;
+        for (int i = 0; i < 6; ++i) R.out->cyc_stage[i] = cyc_stage[i];
+        __threadfence();
+        atomicExch(R.dev_stop, 1);
+    }
+}
+
 struct LzPipeShared {
     double pollsum[4 * 8];
     double coef[8];            // k1, k2, k3, k4, alpha, beta of the phase being finished
@@ -1744,7 +2345,12 @@ struct LzPipeShared {
 // Host contract (setup_persist): every CTA has at most (kPWarps - ceil(ncta / 32)) * 32 rows, so that the last ceil(ncta / 32)
 // warps own no rows and can act as the polling warps.
 template <bool SORTED, int VB>
-__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P) {
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P, RrArgs R) {
+    if (blockIdx.x == (unsigned int)a.ncta) {   // the extra CTA of the launch: on-device Rayleigh-Ritz / stop decision
+        extern __shared__ double rr_smem[];
+        lz_rr_main(R, rr_smem, J.prod_cap + J.prod_cap / 2);
+        return;
+    }
     extern __shared__ double prod[];
     __shared__ double sm[4 * kPWarps];
     __shared__ LzPipeShared sh;
@@ -1988,6 +2594,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
         a.st->cur = cur;
         a.st->beta_prev = sh.beta_prev;
         a.st->usum_prev = sh.usum_prev;
+        if (R.enabled) R.out->phases = phase;
     }
 #undef LZS
 #undef LZLD
@@ -2337,9 +2944,11 @@ __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double*
 __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const double* __restrict__ basis,
                                                  const double* __restrict__ coef, double* __restrict__ out,
                                                  LzScalars* sc, ReduceWS ws,
-                                                 const int* __restrict__ perm /* engine -> caller numbering, or null */) {
+                                                 const int* __restrict__ perm /* engine -> caller numbering, or null */,
+                                                 const RrOut* __restrict__ rr /* k decided on the device, or null */) {
     __shared__ double sm[2 * kWarpsPerBlock];
     __shared__ int flag;
+    if (rr) k = rr->k;
     double r0 = 0.0, r1 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         // newest vectors first: the last ~100 MB the Lanczos kernel wrote are still in L2
@@ -2483,6 +3092,211 @@ __global__ void __launch_bounds__(kBlock) k_sel_pick(SelState* st, int shift) {
         st->eq_total = (long long)h;
     }
     st->hist[t] = 0u;
+}
+
+// ---- K5, two-pass form: one 15-bit histogram of the whole array + an exact select inside the chosen bin ------------------------
+// The eight (histogram, pick) launch pairs above cost more than the eigen-solve on small graphs (17 launches per LP step) and
+// read g eight times.  Here:
+//   k_sel2_hist     ONE pass over g: histogram of the top 15 key bits (sign, exponent, three mantissa bits) in shared memory
+//                   (32 768 bins = 128 KB, one CTA per SM), non-empty bins merged into a global histogram; the last CTA to finish
+//                   walks it from the top and fixes the bin holding the k-th largest key, the rank inside it and the count above;
+//   k_sel2_compact  second pass over g: the keys of that bin (a few per cent of the array) appended to a candidate buffer;
+//   k_sel2_refine   one CTA: the remaining 49 bits by four 13/13/13/10-bit histogram passes over the candidates.
+// Arrays of up to kSel2SmallMax elements do all of it in one single-CTA launch (k_sel2_small).  The result is the same SelState
+// (exact 64-bit key of the k-th element, ties to take, count above, number of ties) the apply kernels below consume.
+constexpr int kSel2Bins = 1 << 15;
+constexpr int kSel2Block = 1024;
+constexpr int kSel2SmallMax = 1 << 16;
+
+struct Sel2State {
+    unsigned int bin;        // top 15 key bits of the k-th largest key
+    unsigned int ncand;      // candidates appended so far (k_sel2_compact)
+    long long remaining;     // rank of the k-th largest key inside the bin, counted from the bin's largest (1-based)
+    long long count_gt;      // keys in bins above
+    unsigned int done;       // CTAs of k_sel2_hist that have merged their histogram
+    unsigned int pad;
+};
+
+// Block-wide (kSel2Block threads): the bin d, counted from the TOP, in which the cumulative count reaches `rem`
+// (above < rem <= above + hist[d]); nbins a multiple of kSel2Block.  Results through shared memory.
+__device__ __forceinline__ void sel2_find_from_top(const unsigned int* hist, int nbins, long long rem, unsigned long long* warp_tot /*[32]*/,
+                                                   int* out_digit, long long* out_above, unsigned int* out_count) {
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = nbins / kSel2Block;
+    unsigned long long tsum = 0;
+    for (int b = 0; b < per; ++b) tsum += hist[tid * per + b];
+    // inclusive suffix sum inside the warp, then the totals of the warps above
+    unsigned long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
+    }
+    if (lane == 0) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long above = incl - tsum;
+    for (int w = warp + 1; w < kSel2Block / 32; ++w) above += warp_tot[w];
+    if ((long long)above < rem && (long long)(above + tsum) >= rem) {
+        unsigned long long a = above;
+        for (int b = per - 1; b >= 0; --b) {
+            const unsigned int h = hist[tid * per + b];
+            if ((long long)(a + h) >= rem) {
+                *out_digit = tid * per + b;
+                *out_above = (long long)a;
+                *out_count = h;
+                break;
+            }
+            a += h;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void sel2_hist_add(unsigned int* sh, unsigned int d, bool ok) {
+    // warp-aggregated update (the leading key bits are nearly constant across the array)
+    const unsigned int peers = __match_any_sync(0xffffffffu, ok ? d : 0xffffffffu);
+    if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[d], (unsigned int)__popc(peers));
+}
+
+__global__ void __launch_bounds__(kSel2Block, 1) k_sel2_hist(int64_t m, const double* __restrict__ g, long long k, unsigned int* __restrict__ ghist,
+                                                              Sel2State* s2) {
+    extern __shared__ unsigned int sh2[];   // [kSel2Bins]
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ int digit;
+    __shared__ long long above_s;
+    __shared__ unsigned int count_s;
+    __shared__ int last;
+    for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) sh2[i] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kSel2Block;
+    const int64_t mceil = ((m + 31) / 32) * 32;
+    for (int64_t e = (int64_t)blockIdx.x * kSel2Block + threadIdx.x; e < mceil; e += stride) {
+        const bool ok = e < m;
+        const unsigned int d = ok ? (unsigned int)(order_key(g[e]) >> 49) : 0u;
+        sel2_hist_add(sh2, d, ok);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) {
+        const unsigned int c = sh2[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&s2->done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) {
+        sh2[i] = __ldcg(ghist + i);
+        ghist[i] = 0u;   // ready for the next selection
+    }
+    __syncthreads();
+    sel2_find_from_top(sh2, kSel2Bins, k, warp_tot, &digit, &above_s, &count_s);
+    if (threadIdx.x == 0) {
+        s2->bin = (unsigned int)digit;
+        s2->remaining = k - above_s;
+        s2->count_gt = above_s;
+        s2->ncand = 0u;
+        s2->done = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_sel2_compact(int64_t m, const double* __restrict__ g, Sel2State* s2,
+                                                         unsigned long long* __restrict__ cand) {
+    const unsigned int bin = s2->bin;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t mceil = ((m + 31) / 32) * 32;
+    const int lane = threadIdx.x & 31;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mceil; e += stride) {
+        unsigned long long key = 0ull;
+        bool hit = false;
+        if (e < m) {
+            key = order_key(g[e]);
+            hit = (unsigned int)(key >> 49) == bin;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            unsigned int base = 0;
+            if (lane == __ffs(bal) - 1) base = atomicAdd(&s2->ncand, (unsigned int)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (hit) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+        }
+    }
+}
+
+// The low 49 key bits of the k-th largest key: four histogram passes (13, 13, 13, 10 bits) over the candidates.
+// FROM_G: the candidates are the elements of g whose top 15 key bits equal the chosen bin (single-CTA path, no compaction).
+template <bool FROM_G>
+__device__ __forceinline__ void sel2_refine_body(int64_t n, const unsigned long long* __restrict__ cand, const double* __restrict__ g,
+                                                 unsigned int bin, long long rem, long long cgt, unsigned int* hist /*[8192]*/,
+                                                 unsigned long long* warp_tot, int* digit, long long* above_s, unsigned int* count_s, SelState* st) {
+    unsigned long long prefix = (unsigned long long)bin << 49, decided = 0x7fffull << 49;
+    unsigned int eq = 0;
+    const int shifts[4] = {36, 23, 10, 0};
+    const int bits[4] = {13, 13, 13, 10};
+    for (int p = 0; p < 4; ++p) {
+        const int nb = 1 << bits[p];
+        for (int i = threadIdx.x; i < 8192; i += kSel2Block) hist[i] = 0u;
+        __syncthreads();
+        const int64_t nceil = ((n + 31) / 32) * 32;
+        for (int64_t i = threadIdx.x; i < nceil; i += kSel2Block) {
+            bool ok = false;
+            unsigned int d = 0;
+            if (i < n) {
+                const unsigned long long key = FROM_G ? order_key(g[i]) : cand[i];
+                ok = (key & decided) == prefix;
+                d = (unsigned int)((key >> shifts[p]) & (unsigned long long)(nb - 1));
+            }
+            sel2_hist_add(hist, d, ok);
+        }
+        __syncthreads();
+        sel2_find_from_top(hist, 8192, rem, warp_tot, digit, above_s, count_s);   // bins >= nb are empty
+        prefix |= (unsigned long long)(*digit) << shifts[p];
+        decided |= (unsigned long long)(nb - 1) << shifts[p];
+        cgt += *above_s;
+        rem -= *above_s;
+        eq = *count_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        st->prefix = prefix;
+        st->mask = ~0ull;
+        st->remaining = rem;
+        st->count_gt = cgt;
+        st->eq_total = (long long)eq;
+    }
+}
+
+__global__ void __launch_bounds__(kSel2Block, 1) k_sel2_refine(const Sel2State* s2, const unsigned long long* __restrict__ cand, SelState* st) {
+    __shared__ unsigned int hist[8192];
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ int digit;
+    __shared__ long long above_s;
+    __shared__ unsigned int count_s;
+    sel2_refine_body<false>((int64_t)s2->ncand, cand, nullptr, s2->bin, s2->remaining, s2->count_gt, hist, warp_tot, &digit, &above_s, &count_s, st);
+}
+
+// Whole selection in one CTA (m <= kSel2SmallMax): 15-bit histogram, pick, four refinement passes straight over g.
+__global__ void __launch_bounds__(kSel2Block, 1) k_sel2_small(int64_t m, const double* __restrict__ g, long long k, SelState* st) {
+    extern __shared__ unsigned int sh2[];   // [kSel2Bins]; its first 8192 words double as the refinement histogram
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ int digit;
+    __shared__ long long above_s;
+    __shared__ unsigned int count_s;
+    for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) sh2[i] = 0u;
+    __syncthreads();
+    const int64_t mceil = ((m + 31) / 32) * 32;
+    for (int64_t e = threadIdx.x; e < mceil; e += kSel2Block) {
+        const bool ok = e < m;
+        const unsigned int d = ok ? (unsigned int)(order_key(g[e]) >> 49) : 0u;
+        sel2_hist_add(sh2, d, ok);
+    }
+    __syncthreads();
+    sel2_find_from_top(sh2, kSel2Bins, k, warp_tot, &digit, &above_s, &count_s);
+    const unsigned int bin = (unsigned int)digit;
+    const long long rem = k - above_s, cgt = above_s;
+    __syncthreads();
+    sel2_refine_body<true>(m, nullptr, g, bin, rem, cgt, sh2, warp_tot, &digit, &above_s, &count_s, st);
 }
 
 // Selection mask + dual-bound term.  Block b owns the contiguous index range [b*chunk, (b+1)*chunk)
