@@ -9,7 +9,7 @@ OUT := mac_b200/libmacb200.so
 all: $(OUT)
 
 $(OUT): $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/macb_ptxas.so $(SRC) 2>&1 | grep -E 'Compiling|registers|spill' 

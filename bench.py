@@ -157,6 +157,70 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ K-sweep (BASELINE configs[3])
+def ksweep(world, rank, local_rank):
+    """sphere2500 + city10000, nine budgets each (10..90 % of the candidates), the protocol of g2o_experiment.py:306-321,
+    farmed one-budget-per-GPU through the C-ABI (`macb_sweep`: longest-first assignment, ONE ncclAllGather of the results).
+    Every rank returns the same dict: seconds per dataset (max over ranks) and the deviation from the reference's own
+    results (tests/golden/g2o_ksweep.json, generated by running the unmodified reference)."""
+    from mac_b200 import farm
+    from mac_b200.g2o import split_edges
+    from mac_b200.solvers import NaiveGreedy
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "g2o_ksweep.json")))
+    comm = farm.farm_comm(local_rank)
+
+    def sync_max(x):
+        return float(comm.allgather(np.array([x])).max()) if comm is not None else float(x)
+
+    out = {}
+    for name in ("sphere2500", "city10000"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", f"g2o_{name}.npz"))
+        fixed, cand = split_edges(z["i"], z["j"], z["kappa"])
+        n, m = int(z["n"]), len(cand[0])
+        budgets = [int(p * m) for p in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)]
+        naive = NaiveGreedy(cand[2])
+        farm.sweep_budgets(fixed, cand, n, budgets, naive.subset, device=local_rank, max_iters=1)   # warm-up: contexts, engines
+        sync_max(0.0)
+        t0 = time.perf_counter()
+        res = farm.sweep_budgets(fixed, cand, n, budgets, naive.subset, device=local_rank, max_iters=20)
+        dt = sync_max(time.perf_counter() - t0)
+        runs = gold[name]["runs"]
+        dlam = [abs(lam - runs[str(k)]["unrounded_l2"]) / runs[str(k)]["unrounded_l2"] for (k, r, w, u, lam) in res]
+        du = [abs(u - runs[str(k)]["u"]) / runs[str(k)]["u"] for (k, r, w, u, lam) in res]
+        out[name] = {"seconds": dt, "budgets": len(budgets), "max_rel_dlambda2_vs_reference": max(dlam),
+                     "median_rel_dlambda2_vs_reference": float(np.median(dlam)), "max_rel_du_vs_reference": max(du),
+                     "selected_ok": all(int(r.sum()) == k for (k, r, w, u, lam) in res)}
+    out["note"] = ("deviations above ~1e-6 come from budgets whose Frank-Wolfe trajectory crosses an LP tie (city10000: all kappa = 100; "
+                   "tests/test_gpu_parity.py asserts the fork happens inside the tie window)")
+    return out
+
+
+def hbm_spmv_point(local_rank, peak):
+    """The HBM-bound SpMV point the north-star asks for: a matrix ten times the L2 (n = 4M, 88M off-diagonals, 1.18 GB
+    algorithmic, band |i - j| <= 2000 like a pose graph), best of the two SpMV kernels, against the measured copy bandwidth."""
+    from mac_b200 import _lib
+    n, m, band = 4_000_000, 40_000_000, 2000
+    rng = np.random.default_rng(0)
+    fi = np.arange(n - 1, dtype=np.int32)
+    a = rng.integers(0, n, size=m, dtype=np.int64)
+    b = a + rng.integers(2, band, size=m, dtype=np.int64)
+    b = np.where(b >= n, a - (b - a), b)
+    ok = np.abs(a - b) > 1
+    ci, cj = a[ok].astype(np.int32), b[ok].astype(np.int32)
+    h = _lib.Handle(n, fi, fi + 1, np.ones(n - 1), ci, cj, np.ones(len(ci)), device=local_rank)
+    h.set_x(np.ones(len(ci)))
+    best = None
+    for engine, name in ((0, "k_spmv"), (1, "k_spmv_jds")):
+        h.spmv_engine(engine)
+        ms, by = h.spmv_bench(20, False)
+        gbs = by / ms / 1e6
+        if best is None or gbs > best["GBs"]:
+            best = {"kernel": name, "GBs": gbs, "frac": gbs / peak, "ms": ms, "algorithmic_GB": by / 1e9, "n": n,
+                    "nnz_offdiag": h.sizes()["nnz_union"], "matrix": f"chain + random candidates with |i-j| <= {band}"}
+    h.close()
+    return best
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args, rank, local_rank, world):
     from mac_b200.solvers import MAC
@@ -221,25 +285,35 @@ def run_ours(args, rank, local_rank, world):
     assert np.array_equal(w, w2)
 
     dev_max, e2e_max = max_over_ranks([dev_s, e2e_s])
+    rr_stats = h.device_rr_stats()
+    sweep = None
+    if not args.no_ksweep:
+        sweep = ksweep(world, rank, local_rank)   # every rank takes part (one budget per GPU, NCCL gather behind the C-ABI)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (CSR SpMV): back-to-back launches on the library stream, CUDA events
+    # ---- roofline of the dominant kernel: the persistent Lanczos kernel, timed live inside the timed region (CUDA events
+    # around its launches on the library stream).  Bytes per step follow the ACTIVE slots of every launch (sum over
+    # launches of steps x bytes(nnz_active), macb_lanczos_kernel_time).
+    from mac_b200 import _lib
     peak, peak_kind = peaks()
+    l2_peak = _lib.measure_l2_bandwidth(local_rank, 24 << 20, 20)
     h.set_x(w)
     spmv_ms, algo_bytes = h.spmv_bench(300, False)
     spmv_cold_ms, _ = h.spmv_bench(30, True)
     sizes = h.sizes()
     spmv_achieved = algo_bytes / (spmv_ms * 1e-3) / 1e9
-    # dominant kernel: the persistent Lanczos kernel, timed live inside the timed region (events around its launches)
     lz_us = lz["ms"] * 1e3 / max(lz["phases"], 1)
     achieved = lz["algo_bytes_per_phase"] / (lz_us * 1e-6) / 1e9 if lz["phases"] else spmv_achieved
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "lanczos_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+    hbm_spmv = None
+    if world == 1 and not args.no_hbm_spmv:
+        hbm_spmv = hbm_spmv_point(local_rank, peak)
 
     line = {
         "metric": METRIC, "value": world * K / dev_max, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -255,24 +329,33 @@ def run_ours(args, rank, local_rank, world):
             "wall_s_timed_region_incl_flush": wall_timed, "final_lambda2": float(info["f_hist"][-1]), "dual_bound": u,
             "spmv_us_l2_resident": spmv_ms * 1e3, "spmv_us_l2_flushed": spmv_cold_ms * 1e3,
             "roofline_peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+            "stop_decision": ("on the device (Rayleigh-Ritz CTA of the Lanczos launch); one host synchronisation per FW iteration"
+                              if rr_stats["enabled"] else "host Rayleigh-Ritz"),
+            "device_rr_fallbacks": rr_stats["fallbacks"],
+            "ksweep": sweep,
         },
         "e2e": {"value": world * K / e2e_max, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * len(x0) / K, "d2h_bytes_per_step": (8 * len(x0) + 16 * K + 16) / K,
                 "api": "MAC.frank_wolfe(k, x_init, max_iters=K) -> macb_fw_run, host numpy buffers"},
         "gpu_launches": counters["kernel_launches"],
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": f"{h.lanczos_kernel_name()}: one launch per eigen-solve; per Lanczos step one SpMV "
-                     "(8-byte gathers from the materialised Lanczos vector, slots in column order), row sums, ONE grid barrier "
-                     "(all-to-all exchange of the partial sums) and a local three-term update", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": f"{h.lanczos_kernel_name()}: one launch per eigen-solve (solver CTAs + one Rayleigh-Ritz "
+                     "CTA); per Lanczos step one SpMV (8-byte gathers of the published vector, slots in column order), row sums along "
+                     "jagged diagonals and a pipelined three-term update whose reduction overlaps the next SpMV",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "us_per_lanczos_step": lz_us, "lanczos_steps_timed": lz["phases"],
                      "share_of_timed_region": lz["ms"] / (dev_max * 1e3),
                      "algorithmic_bytes_per_step": lz["algo_bytes_per_phase"],
+                     "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                            "what": "the same algorithmic bytes against the L2 -> SM read bandwidth measured in this run "
+                                    "(macb_measure_l2_bandwidth: all SMs streaming a 24 MB L2-resident buffer); the matrix is "
+                                    "L2-resident, so this is the bound that binds"},
                      "standalone_spmv": {"kernel": "k_spmv", "achieved": spmv_achieved, "frac": spmv_achieved / peak},
-                     "note": "achieved = algorithmic bytes per Lanczos step x steps / CUDA-event time of the kernel launches inside "
-                             "the timed region. The 29.6 MB matrix is L2-resident (traffic = measured DRAM bytes per step) and the "
-                             "access pattern is one random gather per non-zero, so the binding limit is the L1TEX wavefront rate "
-                             "(one 128-byte line per clock and SM, tools/micro/gather_mix.cu), not HBM: see DESIGN.md section 5"},
+                     "hbm_spmv": hbm_spmv,
+                     "note": "achieved = algorithmic bytes (active slots) x steps / CUDA-event time of the kernel launches inside the "
+                             "timed region. The 29.6 MB matrix is L2-resident (traffic = DRAM bytes per step of the ncu --set full "
+                             "capture under profiles/), every gather moves a 32-byte L2 sector for 8 useful bytes, and pass 1 of a step "
+                             "runs at ~70 % of the measured L2 bandwidth in sector traffic: see DESIGN.md section 5"},
     }
     if world == 1 and not args.no_cpu_baseline:
         fixed0, cand0, n0, k0, x00 = (fixed, cand, n, k, x0)
@@ -310,6 +393,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--cpu-baseline-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ksweep", action="store_true", help="skip the sphere2500 + city10000 budget sweep (config.ksweep)")
+    ap.add_argument("--no-hbm-spmv", action="store_true", help="skip the 1.18 GB HBM-bound SpMV point (roofline.hbm_spmv)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -180,6 +180,34 @@ int macb_device_rr_stats(macb_handle h, int* enabled, int64_t* fallbacks, int* l
 /* cudaDeviceSynchronize on the handle's device. */
 int macb_device_sync(macb_handle h);
 
+/* ---- K-sweep farm (multi-GPU) ----------------------------------------------------------------- */
+
+/* The budget sweep of examples/g2o_experiment.py:284,306-336 has no loop-carried state: rank r of a group of processes (one
+ * per GPU, every rank holding the same graph in its own handle) takes its share of the budgets, and ONE ncclAllGather of
+ * fixed-size records collects the results on every rank.  NCCL is loaded at run time (dlopen of libnccl.so.2, or
+ * $MACB_NCCL_LIB); the 128-byte unique id of macb_comm_unique_id (rank 0) reaches the other ranks by whatever out-of-band
+ * channel the launcher has (mac_b200/farm.py: a TCP socket on MASTER_ADDR). */
+typedef struct macb_comm* macb_comm_t;
+int macb_comm_unique_id(char* id /*[128]*/);
+int macb_comm_init(int nranks, int rank, const char* id /*[128]*/, int device, macb_comm_t* out);
+/* send[bytes_per_rank] (host) from every rank -> recv[nranks * bytes_per_rank] (host) on every rank. */
+int macb_comm_allgather(macb_comm_t c, const void* send, void* recv, int64_t bytes_per_rank);
+int macb_comm_destroy(macb_comm_t c);
+const char* macb_comm_last_error(macb_comm_t c);
+
+/* owner[i] = rank that solves budget ks[i]: longest-processing-time-first on the cost estimate 1 + (m - k)/m (low budgets
+ * run all their Frank-Wolfe iterations, high budgets exit early). */
+int macb_sweep_owner(const int64_t* ks, int nk, int64_t m, int nranks, int32_t* owner);
+
+/* For every budget ks[i], i < nk: MAC.solve(ks[i], x_inits[i], max_iters, rounding="nearest") as g2o_experiment.py:319 calls it
+ * (mac.py:130-225), plus lambda2 of the relaxed solution (g2o_experiment.py:347).  comm == NULL: this process solves all of
+ * them; otherwise every rank of `comm` calls this with the same arguments, solves the budgets macb_sweep_owner gives it and
+ * receives all results.  x_inits[nk][m]; out: rounded[nk][m] (0/1), w[nk][m] (relaxed solutions, may be NULL), u[nk] (dual
+ * bounds), lambda_unrounded[nk], iters[nk]. */
+int macb_sweep(macb_handle h, macb_comm_t comm, const int64_t* ks, int nk, const double* x_inits, int max_iters,
+               double rel_gap_tol, double grad_norm_tol, double fiedler_tol, double min_sel_tol, int fiedler_max_steps,
+               uint8_t* rounded, double* w, double* u, double* lambda_unrounded, int32_t* iters);
+
 /* ---- host-only helpers (no GPU needed; exported for the CPU test-suite) ----------------------- */
 
 /* Host-side layout builder of the Lanczos kernels (jagged diagonals, column-sorted slots, bank-fitted product positions;

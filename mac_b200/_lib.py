@@ -80,6 +80,14 @@ def lib():
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
     _sig(L.macb_host_build_jds, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int32, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip])
+    _sig(L.macb_comm_unique_id, [C.c_char_p])
+    _sig(L.macb_comm_init, [C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(H)])
+    _sig(L.macb_comm_allgather, [H, C.c_void_p, C.c_void_p, C.c_int64])
+    _sig(L.macb_comm_destroy, [H])
+    _sig(L.macb_comm_last_error, [H], C.c_char_p)
+    _sig(L.macb_sweep_owner, [_lp, C.c_int, C.c_int64, C.c_int, _ip])
+    _sig(L.macb_sweep, [H, H, _lp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                        C.POINTER(C.c_uint8), _dp, _dp, _dp, _ip])
     _sig(L.macb_device_rr_stats, [H, C.POINTER(C.c_int), _lp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp])
     _sig(L.macb_measure_l2_bandwidth, [C.c_int, C.c_int64, C.c_int, _dp])
     _sig(L.macb_version, [], C.c_char_p)
@@ -106,6 +114,49 @@ def measure_l2_bandwidth(device=-1, nbytes=24 << 20, reps=20):
     if rc != MACB_OK:
         raise MacbError(f"macb_measure_l2_bandwidth failed ({rc}): {lib().macb_last_error(None).decode()}")
     return out.value
+
+
+def sweep_owner(budgets, m, nranks):
+    """Rank that solves each budget (host-only: macb_sweep_owner)."""
+    ks = np.ascontiguousarray(budgets, dtype=np.int64)
+    owner = np.zeros(len(ks), dtype=np.int32)
+    rc = lib().macb_sweep_owner(_p(ks, _lp), len(ks), int(m), int(nranks), _p(owner, _ip))
+    if rc != MACB_OK:
+        raise MacbError(f"macb_sweep_owner failed ({rc})")
+    return owner
+
+
+class Comm:
+    """NCCL communicator of the K-sweep farm (macb_comm_*): one per process, created from a 128-byte unique id."""
+
+    def __init__(self, nranks, rank, unique_id, device=-1):
+        self._L = lib()
+        self._c = C.c_void_p()
+        self.nranks, self.rank = int(nranks), int(rank)
+        rc = self._L.macb_comm_init(self.nranks, self.rank, unique_id, int(device), C.byref(self._c))
+        if rc != MACB_OK:
+            raise MacbError(f"macb_comm_init failed ({rc}): {self._L.macb_last_error(None).decode()}")
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = lib().macb_comm_unique_id(buf)
+        if rc != MACB_OK:
+            raise MacbError(f"macb_comm_unique_id failed ({rc}): {lib().macb_last_error(None).decode()}")
+        return buf.raw
+
+    def allgather(self, arr):
+        arr = np.ascontiguousarray(arr)
+        out = np.empty((self.nranks,) + arr.shape, dtype=arr.dtype)
+        rc = self._L.macb_comm_allgather(self._c, arr.ctypes.data, out.ctypes.data, arr.nbytes)
+        if rc != MACB_OK:
+            raise MacbError(f"macb_comm_allgather failed ({rc}): {self._L.macb_comm_last_error(self._c).decode()}")
+        return out
+
+    def close(self):
+        if self._c:
+            self._L.macb_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 class Handle:
@@ -219,6 +270,23 @@ class Handle:
         self._check(rc, "macb_fw_run")
         it = iters.value
         return w, u.value, {"iters": it, "f_hist": fh[:it].copy(), "u_hist": uh[:it].copy()}
+
+    def sweep(self, comm, budgets, x_inits, max_iters=20, rel_gap_tol=1e-4, grad_norm_tol=1e-8, fiedler_tol=1e-8, min_sel_tol=1e-10,
+              fiedler_max_steps=0, want_w=True):
+        """macb_sweep: the g2o budget sweep, this rank's share solved here, results gathered over `comm` (None: single process)."""
+        ks = np.ascontiguousarray(budgets, dtype=np.int64)
+        nk = len(ks)
+        x_inits = np.ascontiguousarray(x_inits, dtype=np.float64).reshape(nk, self.m)
+        rounded = np.zeros((nk, self.m), dtype=np.uint8)
+        w = np.zeros((nk, self.m)) if want_w else None
+        u, lam = np.zeros(nk), np.zeros(nk)
+        iters = np.zeros(nk, dtype=np.int32)
+        rc = self._L.macb_sweep(self._h, comm._c if comm is not None else None, _p(ks, _lp), nk, _p(x_inits, _dp), int(max_iters),
+                                float(rel_gap_tol), float(grad_norm_tol), float(fiedler_tol), float(min_sel_tol), int(fiedler_max_steps),
+                                rounded.ctypes.data_as(C.POINTER(C.c_uint8)), _p(w, _dp) if want_w else None, _p(u, _dp), _p(lam, _dp),
+                                _p(iters, _ip))
+        self._check(rc, "macb_sweep")
+        return rounded, w, u, lam, iters
 
     # -- measurement
     def counters(self):

@@ -18,6 +18,7 @@
 #include <vector>
 #include <chrono>
 #include <thread>
+#include <dlfcn.h>
 
 #include "kernels.cuh"
 #include "tridiag.h"
@@ -53,6 +54,19 @@ struct ArgFail {
     std::string msg;
     int code;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION, shared by every handle in the process: only ever
+// raise it (a handle with a small graph must not lower it under a handle with a large one -- the cooperative launch of the
+// large one then fails with "too many blocks").
+void raise_dyn_smem(const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> cur;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& c = cur[fn];
+    if (bytes <= c) return;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c = bytes;
+}
 
 template <typename T>
 T* dalloc(size_t count) {
@@ -622,8 +636,8 @@ void setup_persist(macb_ctx* c) {
         c->persist_v = 4;
         c->p_ncta = 1;
         c->slots_smem = small_bytes;
-        CK(cudaFuncSetAttribute((const void*)k_lanczos_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
-        CK(cudaFuncSetAttribute((const void*)k_lanczos_small2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+        raise_dyn_smem((const void*)k_lanczos_small, (size_t)(small_bytes));
+        raise_dyn_smem((const void*)k_lanczos_small2, (size_t)(small_bytes));
         c->small_v2 = !getenv("MACB_SMALL_V1");
         rs.assign(2, n);
         rs[0] = 0;
@@ -682,7 +696,7 @@ void setup_persist(macb_ctx* c) {
                 c->slots_cache_cols = 1;
                 c->slots_smem = (size_t)max_slots * 12;
             }
-            CK(cudaFuncSetAttribute((const void*)k_lanczos_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+            raise_dyn_smem((const void*)k_lanczos_slots, (size_t)(c->slots_smem));
             // jagged-diagonal staging (k_lanczos_jds): one chunk per CTA, products + column cache + diagonal starts fit
             const int64_t cap4 = std::max<int64_t>((max_slots + 3) / 4 * 4, kPBlock);   // >= kPBlock: prod[0 + tid] is always addressable
             const int64_t stride = (maxrow + 8 + 3) / 4 * 4;   // + 8: k_lanczos_vec reads the diagonal starts eight at a time
@@ -717,14 +731,14 @@ void setup_persist(macb_ctx* c) {
                     for (int b = 0; b < ncta; ++b) maxrows = std::max(maxrows, rs[b + 1] - rs[b]);
                     c->pipe = !getenv("MACB_NO_PIPE") && ncta <= 256 && maxrows <= (kPWarps - (ncta + 31) / 32) * 32;
                 }
-                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
-                CK(cudaFuncSetAttribute((const void*)k_lanczos_jds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));
+                raise_dyn_smem((const void*)k_lanczos_jds<false>, (size_t)(c->slots_smem));
+                raise_dyn_smem((const void*)k_lanczos_jds<true>, (size_t)(c->slots_smem));
 #define MACB_VEC_SMEM(VB_)                                                                                                                   \
-    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<false, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem)); \
-    CK(cudaFuncSetAttribute((const void*)k_lanczos_vec<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slots_smem));  \
+    raise_dyn_smem((const void*)k_lanczos_vec<false, VB_>, c->slots_smem); \
+    raise_dyn_smem((const void*)k_lanczos_vec<true, VB_>, c->slots_smem);  \
     if (c->pipe) {                                                                                                                        \
-        CK(cudaFuncSetAttribute((const void*)k_lanczos_pipe<false, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->pipe_smem)); \
-        CK(cudaFuncSetAttribute((const void*)k_lanczos_pipe<true, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->pipe_smem));  \
+        raise_dyn_smem((const void*)k_lanczos_pipe<false, VB_>, c->pipe_smem); \
+        raise_dyn_smem((const void*)k_lanczos_pipe<true, VB_>, c->pipe_smem);  \
     }
                 MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
 #undef MACB_VEC_SMEM
@@ -1588,8 +1602,8 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         c->d_sel_cand = dalloc<unsigned long long>(m);
         CK(cudaMemsetAsync(c->d_sel2_hist, 0, kSel2Bins * sizeof(unsigned int), c->stream));
         CK(cudaMemsetAsync(c->d_sel2, 0, sizeof(Sel2State), c->stream));
-        CK(cudaFuncSetAttribute((const void*)k_sel2_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSel2Bins * sizeof(unsigned int))));
-        CK(cudaFuncSetAttribute((const void*)k_sel2_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSel2Bins * sizeof(unsigned int))));
+        raise_dyn_smem((const void*)k_sel2_hist, (size_t)(kSel2Bins * sizeof(unsigned int)));
+        raise_dyn_smem((const void*)k_sel2_small, (size_t)(kSel2Bins * sizeof(unsigned int)));
         c->topk8 = getenv("MACB_TOPK8") != nullptr;
         CK(cudaMallocHost(&c->h_sc, sizeof(LzScalars)));
         CK(cudaMallocHost(&c->h_sel_state, sizeof(SelState)));
@@ -2259,6 +2273,258 @@ int macb_spmv_bench(macb_handle h, int reps, int flush_l2, double* avg_ms, doubl
         if (algo_bytes) *algo_bytes = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n;
         return (int)MACB_OK;
     });
+}
+
+}  // extern "C"
+
+// ================================================================================================ K-sweep farm (NCCL)
+// One process per GPU; every rank holds the same graph and takes its share of the budgets; the ONLY
+// communication is one ncclAllGather of fixed-size result records at the end.  NCCL is loaded at run time (dlopen), so the
+// library itself links against nothing but the CUDA runtime and still loads on a box without NCCL.
+struct NcclId { char bytes[128]; };   // ncclUniqueId: passed BY VALUE to ncclCommInitRank
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+bool load_nccl(std::string& err) {
+    std::lock_guard<std::mutex> lk(g_nccl_mutex);
+    if (g_nccl.lib) return true;
+    const char* names[] = {getenv("MACB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) {
+        if (!nm) continue;
+        lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        err = "NCCL not found (dlopen libnccl.so.2 failed; set MACB_NCCL_LIB)";
+        return false;
+    }
+    NcclApi a;
+    a.lib = lib;
+    a.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    a.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) {
+        err = "NCCL library lacks an expected symbol";
+        dlclose(lib);
+        return false;
+    }
+    g_nccl = a;
+    return true;
+}
+
+// longest-processing-time-first assignment of the budgets to ranks (the same rule as mac_b200/farm.py:assign)
+std::vector<int> sweep_owner(const int64_t* ks, int nk, int64_t m, int nranks) {
+    std::vector<double> cost(nk);
+    for (int i = 0; i < nk; ++i) cost[i] = 1.0 + (double)(m - ks[i]) / (double)std::max<int64_t>(m, 1);
+    std::vector<int> order(nk), owner(nk, 0);
+    for (int i = 0; i < nk; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<double> load(nranks, 0.0);
+    for (int i : order) {
+        int r = 0;
+        for (int q = 1; q < nranks; ++q)
+            if (load[q] < load[r]) r = q;
+        owner[i] = r;
+        load[r] += cost[i];
+    }
+    return owner;
+}
+}  // namespace
+
+struct macb_comm {
+    void* comm = nullptr;
+    int nranks = 1, rank = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+};
+
+extern "C" {
+
+int macb_comm_unique_id(char* id /*[128]*/) {
+    std::string err;
+    if (!id) return MACB_ERR_ARG;
+    if (!load_nccl(err)) {
+        g_create_error = err;
+        return MACB_ERR_STATE;
+    }
+    NcclId u;
+    memset(&u, 0, sizeof(u));
+    const int rc = g_nccl.GetUniqueId(&u);
+    if (rc != 0) {
+        g_create_error = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+        return MACB_ERR_CUDA;
+    }
+    memcpy(id, u.bytes, 128);
+    return MACB_OK;
+}
+
+int macb_comm_init(int nranks, int rank, const char* id, int device, macb_comm_t* out) {
+    if (!out || !id || nranks < 1 || rank < 0 || rank >= nranks) return MACB_ERR_ARG;
+    *out = nullptr;
+    std::string err;
+    if (!load_nccl(err)) {
+        g_create_error = err;
+        return MACB_ERR_STATE;
+    }
+    macb_comm* c = new macb_comm();
+    c->nranks = nranks;
+    c->rank = rank;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "macb_comm_init: cannot select the device / create a stream";
+        cudaGetLastError();
+        delete c;
+        return MACB_ERR_CUDA;
+    }
+    NcclId u;
+    memcpy(u.bytes, id, 128);
+    const int rc = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
+    if (rc != 0) {
+        g_create_error = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return MACB_ERR_CUDA;
+    }
+    *out = c;
+    return MACB_OK;
+}
+
+int macb_comm_allgather(macb_comm_t c, const void* send, void* recv, int64_t bytes_per_rank) {
+    if (!c || !send || !recv || bytes_per_rank < 0) return MACB_ERR_ARG;
+    if (bytes_per_rank == 0) return MACB_OK;
+    void *dsend = nullptr, *drecv = nullptr;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&dsend, (size_t)bytes_per_rank);
+    if (e == cudaSuccess) e = cudaMalloc(&drecv, (size_t)bytes_per_rank * c->nranks);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dsend, send, (size_t)bytes_per_rank, cudaMemcpyHostToDevice, c->stream);
+    int nrc = 0;
+    if (e == cudaSuccess) nrc = g_nccl.AllGather(dsend, drecv, (size_t)bytes_per_rank, /* ncclUint8 */ 1, c->comm, c->stream);
+    if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(recv, drecv, (size_t)bytes_per_rank * c->nranks, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && nrc == 0) e = cudaStreamSynchronize(c->stream);
+    if (dsend) cudaFree(dsend);
+    if (drecv) cudaFree(drecv);
+    if (nrc != 0) {
+        c->err = std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error");
+        return MACB_ERR_CUDA;
+    }
+    if (e != cudaSuccess) {
+        c->err = std::string("macb_comm_allgather: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return MACB_ERR_CUDA;
+    }
+    return MACB_OK;
+}
+
+int macb_comm_destroy(macb_comm_t c) {
+    if (!c) return MACB_OK;
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MACB_OK;
+}
+
+const char* macb_comm_last_error(macb_comm_t c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int macb_sweep_owner(const int64_t* ks, int nk, int64_t m, int nranks, int32_t* owner) {
+    if (!ks || !owner || nk < 0 || nranks < 1) return MACB_ERR_ARG;
+    std::vector<int> o = sweep_owner(ks, nk, m, nranks);
+    for (int i = 0; i < nk; ++i) owner[i] = o[i];
+    return MACB_OK;
+}
+
+int macb_sweep(macb_handle h, macb_comm_t comm, const int64_t* ks, int nk, const double* x_inits, int max_iters,
+               double rel_gap_tol, double grad_norm_tol, double fiedler_tol, double min_sel_tol, int fiedler_max_steps,
+               uint8_t* rounded, double* w, double* u, double* lambda_unrounded, int32_t* iters) {
+    if (!h) return MACB_ERR_ARG;
+    if (!ks || nk < 0 || (!x_inits && nk > 0 && h->m > 0) || !rounded || !u || !lambda_unrounded || !iters) {
+        h->err = "macb_sweep: NULL argument";
+        return MACB_ERR_ARG;
+    }
+    const int nranks = comm ? comm->nranks : 1, rank = comm ? comm->rank : 0;
+    const int64_t m = h->m;
+    const std::vector<int> owner = sweep_owner(ks, nk, m, nranks);
+    // fixed-size record per budget: rounded mask (m bytes, padded to 8), then w (m doubles, optional), then u, lambda2, iters
+    const int64_t mpad = (m + 7) / 8 * 8;
+    const int64_t rec = mpad + (w ? 8 * m : 0) + 24;
+    int per_rank = 0;
+    {
+        std::vector<int> cnt(nranks, 0);
+        for (int i = 0; i < nk; ++i) per_rank = std::max(per_rank, ++cnt[owner[i]]);
+    }
+    std::vector<uint8_t> mine((size_t)std::max<int64_t>(rec * per_rank, 1), 0);
+    std::vector<double> wbuf((size_t)std::max<int64_t>(m, 1)), rbuf((size_t)std::max<int64_t>(m, 1));
+    int slot = 0, status = MACB_OK;
+    for (int i = 0; i < nk; ++i) {
+        if (owner[i] != rank) continue;
+        if (ks[i] < 0 || ks[i] > m) {
+            h->err = "macb_sweep: budget out of range";
+            return MACB_ERR_ARG;
+        }
+        double ui = 0.0, lam = 0.0;
+        int it = 0;
+        // the g2o protocol (g2o_experiment.py:306-321): MAC.solve(K, x_init, max_iters, rounding='nearest')
+        if (ks[i] >= m) {   // mac.py:173-180
+            std::fill(wbuf.begin(), wbuf.end(), 1.0);
+            std::fill(rbuf.begin(), rbuf.end(), 1.0);
+            int rc = macb_set_x(h, wbuf.data(), min_sel_tol);
+            if (rc == MACB_OK) rc = macb_fiedler(h, fiedler_tol, fiedler_max_steps, 0, &lam, nullptr, nullptr, nullptr);
+            if (rc < 0) return rc;
+            ui = lam;
+        } else {
+            int rc = macb_fw_run(h, ks[i], x_inits + (size_t)i * m, max_iters, rel_gap_tol, grad_norm_tol, fiedler_tol, min_sel_tol,
+                                 fiedler_max_steps, 0, wbuf.data(), &ui, &it, nullptr, nullptr);
+            if (rc < 0) return rc;
+            if (rc == MACB_NOT_CONVERGED) status = rc;
+            rc = macb_round_nearest(h, wbuf.data(), ks[i], 10, rbuf.data());
+            if (rc < 0) return rc;
+            rc = macb_set_x(h, wbuf.data(), min_sel_tol);
+            if (rc == MACB_OK) rc = macb_fiedler(h, fiedler_tol, fiedler_max_steps, 0, &lam, nullptr, nullptr, nullptr);
+            if (rc < 0) return rc;
+        }
+        uint8_t* p = mine.data() + (size_t)slot * rec;
+        for (int64_t e = 0; e < m; ++e) p[e] = rbuf[e] != 0.0 ? 1 : 0;
+        if (w) memcpy(p + mpad, wbuf.data(), (size_t)8 * m);
+        double tail[3] = {ui, lam, (double)it};
+        memcpy(p + mpad + (w ? 8 * m : 0), tail, 24);
+        ++slot;
+    }
+    std::vector<uint8_t> all;
+    const uint8_t* src = mine.data();
+    if (comm && nranks > 1) {
+        all.resize((size_t)rec * per_rank * nranks);
+        const int rc = macb_comm_allgather(comm, mine.data(), all.data(), rec * per_rank);
+        if (rc != MACB_OK) {
+            h->err = comm->err;
+            return rc;
+        }
+        src = all.data();
+    }
+    std::vector<int> next(nranks, 0);
+    for (int i = 0; i < nk; ++i) {
+        const int r = owner[i];
+        const uint8_t* p = src + ((size_t)(nranks > 1 && comm ? r : 0) * per_rank + next[r]++) * rec;
+        memcpy(rounded + (size_t)i * m, p, (size_t)m);
+        if (w) memcpy(w + (size_t)i * m, p + mpad, (size_t)8 * m);
+        double tail[3];
+        memcpy(tail, p + mpad + (w ? 8 * m : 0), 24);
+        u[i] = tail[0];
+        lambda_unrounded[i] = tail[1];
+        iters[i] = (int32_t)tail[2];
+    }
+    return status;
 }
 
 }  // extern "C"

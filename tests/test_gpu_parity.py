@@ -598,42 +598,48 @@ def test_zero_candidates_lp_and_fw_do_not_crash():
 
 
 # ------------------------------------------------------------------------------------------- farm (multi-GPU)
-def _farm_rank(rank, world, port, q):
-    import torch
-    import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
-        from mac_b200 import farm
-        fixed, cand, n = synth.chain_plus_random(1500, 9000, seed=4, weighted=True)
-        budgets = [900, 1800, 2700, 3600]
-        res = farm.sweep_budgets(fixed, cand, n, budgets, lambda k: synth.first_k_init(9000, k), max_iters=5)
-        q.put((rank, [(k, int(r.sum()), float(u), float(lam)) for (k, r, w, u, lam) in res]))
-    finally:
-        dist.destroy_process_group()
+def _run_farm_ranks(world):
+    """`world` processes, one per GPU, each running tools/farm_check.py (macb_sweep + ncclAllGather behind the C-ABI)."""
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tools", "farm_check.py")], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        outs.append(json.loads(out.strip().splitlines()[-1]))
+    return outs
+
+
+def test_farm_sweep_single_process_matches_solve():
+    """macb_sweep without a communicator == MAC.solve budget by budget."""
+    from mac_b200 import farm
+    fixed, cand, n = synth.chain_plus_random(1500, 9000, seed=4, weighted=True)
+    budgets = [900, 1800, 9000, 3600]
+    res = farm.sweep_budgets(fixed, cand, n, budgets, lambda k: synth.first_k_init(9000, k), max_iters=5, comm=None)
+    mac = MAC(fixed, cand, n)
+    for (k, r, w, u, lam) in res:
+        r1, w1, u1 = mac.solve(k, synth.first_k_init(9000, k), max_iters=5)
+        assert np.array_equal(r, r1.astype("u1")) and np.array_equal(w, w1) and u == u1
+        assert abs(lam - mac.evaluate_objective(w1)) <= 1e-12 * lam
+    mac.close()
 
 
 def test_farm_sweep_two_gpus_nccl():
-    """One budget sweep farmed over two GPUs (NCCL gather of the per-budget results) equals the single-GPU sweep."""
+    """One budget sweep farmed over two GPUs (one ncclAllGather of the per-budget records, no torch) equals the single-GPU sweep."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    import socket
-    import torch.multiprocessing as mp
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_farm_rank, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    out = sorted(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert out[0][1] == out[1][1]
-    from mac_b200 import farm
-    fixed, cand, n = synth.chain_plus_random(1500, 9000, seed=4, weighted=True)
-    single = farm.sweep_budgets(fixed, cand, n, [900, 1800, 2700, 3600], lambda k: synth.first_k_init(9000, k), max_iters=5)
-    for (k, nsel, u, lam), (k1, r1, w1, u1, lam1) in zip(out[0][1], single):
-        assert k == k1 and nsel == k and abs(u - u1) <= 1e-9 * abs(u1) and abs(lam - lam1) <= 1e-9 * lam1
+    outs = _run_farm_ranks(2)
+    assert outs[0]["results"] == outs[1]["results"] and {o["rank"] for o in outs} == {0, 1}
+    single = _run_farm_ranks(1)[0]["results"]
+    for a_, b_ in zip(outs[0]["results"], single):
+        assert a_[0] == b_[0] and a_[1] == b_[1] == a_[0]
+        assert abs(a_[2] - b_[2]) <= 1e-12 * abs(b_[2]) and abs(a_[3] - b_[3]) <= 1e-12 * b_[3] and abs(a_[4] - b_[4]) <= 1e-9 * b_[4]

@@ -297,3 +297,36 @@ def test_jagged_diagonal_layout_on_ragged_random_graphs():
                 triples = sorted(zip(rows.tolist(), jrow[cols].tolist(), jeid[sa:sa + ns].tolist()))
                 ref = sorted((r, int(col[s_]), int(eid[s_])) for r in range(ra, rb) for s_ in range(rp[r], rp[r + 1]))
                 assert triples == ref, (trial, b, sorted_slots)
+
+
+def test_sweep_owner_matches_python_assignment():
+    """macb_sweep_owner (the C-ABI's longest-first assignment of budgets to ranks) == farm.assign on the same costs."""
+    from mac_b200 import farm
+    m = 10688
+    budgets = [int(p * m) for p in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)]
+    for world in (1, 2, 3, 4, 8, 16):
+        owner = _lib.sweep_owner(budgets, m, world)
+        parts = farm.assign([1.0 + (m - k) / m for k in budgets], world)
+        for r, idxs in enumerate(parts):
+            assert all(owner[i] == r for i in idxs)
+        assert sorted(i for p in parts for i in p) == list(range(len(budgets)))
+
+
+def test_unique_id_exchange_over_tcp():
+    """The out-of-band channel of the farm (rank 0 -> everybody, 128 bytes over a socket; no torch, no GPU)."""
+    import socket
+    import threading
+    from mac_b200 import farm
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    uid = bytes(range(128))
+    got = {}
+
+    def run(rank):
+        got[rank] = farm.exchange_unique_id(rank, 3, addr="127.0.0.1", port=port, make_id=lambda: uid, timeout=30)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in (1, 2, 0)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=60)
+    assert got == {0: uid, 1: uid, 2: uid}
