@@ -475,8 +475,20 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.stop = async ? c->h_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
     if (c->persist_v == 4) {
-        if (c->small_v2) k_lanczos_small2<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
-        else k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        if (c->small_v2) {
+            RrArgs R = c->rr_launch;
+            R.smem_doubles = (int)(c->slots_smem / 8);
+            if (R.enabled) {
+                a.ab_host = nullptr;
+                a.stop = nullptr;
+            }
+            const double* dg = c->d_diag;
+            void* sparams[] = {&a, &dg, &R};
+            // cooperative: the solver CTA and the Rayleigh-Ritz CTA must be co-resident (the second stops the first)
+            CK(cudaLaunchCooperativeKernel((void*)k_lanczos_small2, dim3(R.enabled ? 2 : 1), dim3(kPBlock), sparams, c->slots_smem, c->stream));
+        } else {
+            k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        }
         CK(cudaGetLastError());
     } else if (c->persist_v == 5) {
         LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
@@ -486,6 +498,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         if (c->jds_vec && c->pipe) {
             LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
             RrArgs R = c->rr_launch;
+            R.smem_doubles = (int)(c->pipe_smem / 8);
             if (R.enabled) {   // device-side decision: nothing is streamed to, or polled from, the host
                 a.ab_host = nullptr;
                 a.stop = nullptr;
@@ -626,6 +639,26 @@ void build_jds_layout(int n, const int32_t* rp, const int32_t* col, const int32_
     }
 }
 
+// Buffers of the on-device Rayleigh-Ritz (lz_rr_main): private copies of T_k, work arrays, result record, stop flag.
+void alloc_device_rr(macb_ctx* c) {
+    if (c->dev_rr || getenv("MACB_HOST_RR")) return;
+    const size_t cap2 = (size_t)c->basis_cap + 4;
+    c->d_rr_a = dalloc<double>(cap2);
+    c->d_rr_b = dalloc<double>(cap2);
+    c->d_rr_b2 = dalloc<double>(cap2);
+    c->d_rr_binv = dalloc<double>(cap2);
+    c->d_rr_s = dalloc<double>(cap2);
+    c->d_rr_w = dalloc<double>(4 * cap2);
+    c->d_rr_out = dalloc<RrOut>(1);
+    c->d_dev_stop = dalloc<int>(1);
+    CK(cudaMallocHost(&c->h_rr, sizeof(RrOut)));
+    CK(cudaMemsetAsync(c->d_dev_stop, 0, sizeof(int), c->stream));
+    c->dev_rr = true;
+}
+size_t rr_smem_bytes(const macb_ctx* c) {
+    return std::min<size_t>((size_t)220 * 1024, (size_t)64 * ((size_t)c->basis_cap + 32));
+}
+
 void setup_persist(macb_ctx* c) {
     const int n = c->n, W = c->W;
     std::vector<int> rs;
@@ -636,9 +669,13 @@ void setup_persist(macb_ctx* c) {
         c->persist_v = 4;
         c->p_ncta = 1;
         c->slots_smem = small_bytes;
-        raise_dyn_smem((const void*)k_lanczos_small, (size_t)(small_bytes));
-        raise_dyn_smem((const void*)k_lanczos_small2, (size_t)(small_bytes));
         c->small_v2 = !getenv("MACB_SMALL_V1");
+        if (c->small_v2) {
+            alloc_device_rr(c);
+            if (c->dev_rr) c->slots_smem = std::max(small_bytes, rr_smem_bytes(c));
+        }
+        raise_dyn_smem((const void*)k_lanczos_small, (size_t)(small_bytes));
+        raise_dyn_smem((const void*)k_lanczos_small2, c->slots_smem);
         rs.assign(2, n);
         rs[0] = 0;
     }
@@ -741,7 +778,6 @@ void setup_persist(macb_ctx* c) {
         raise_dyn_smem((const void*)k_lanczos_pipe<true, VB_>, c->pipe_smem);  \
     }
                 MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
-#undef MACB_VEC_SMEM
                 {   // gathers in flight per thread: the batch size whose last batch of a step is fullest (see kernels.cuh)
                     const double pt = (double)max_slots / (double)kPBlock;
                     double best = -1.0;
@@ -760,19 +796,11 @@ void setup_persist(macb_ctx* c) {
                 }
                 c->jds_vec = !getenv("MACB_NO_VEC");
                 c->d_zprev = dalloc<double>((size_t)n);
-                if (c->pipe && !getenv("MACB_HOST_RR")) {
-                    const size_t cap2 = (size_t)c->basis_cap + 4;
-                    c->d_rr_a = dalloc<double>(cap2);
-                    c->d_rr_b = dalloc<double>(cap2);
-                    c->d_rr_b2 = dalloc<double>(cap2);
-                    c->d_rr_binv = dalloc<double>(cap2);
-                    c->d_rr_s = dalloc<double>(cap2);
-                    c->d_rr_w = dalloc<double>(4 * cap2);
-                    c->d_rr_out = dalloc<RrOut>(1);
-                    c->d_dev_stop = dalloc<int>(1);
-                    CK(cudaMallocHost(&c->h_rr, sizeof(RrOut)));
-                    CK(cudaMemsetAsync(c->d_dev_stop, 0, sizeof(int), c->stream));
-                    c->dev_rr = true;
+                if (c->pipe) {
+                    alloc_device_rr(c);
+                    // the Rayleigh-Ritz CTA keeps T_k (seven arrays) in the launch's dynamic shared memory while it fits
+                    c->pipe_smem = std::max(c->pipe_smem, rr_smem_bytes(c));
+                    MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
                 }
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {
@@ -1131,16 +1159,26 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
 // (solver CTAs + the Rayleigh-Ritz CTA that stops them) -> Ritz vector with the order k and the coefficients the device left
 // -> normalisation -> Rayleigh quotient and the reference's residual (nx:243).  The caller synchronises when IT needs the
 // numbers (macb_fw_run: once per Frank-Wolfe iteration) and then calls finish_fiedler_device.
-bool device_fiedler_available(const macb_ctx* c) { return c->persist && c->persist_v == 5 && c->jds_vec && c->pipe && c->dev_rr; }
+bool device_fiedler_available(const macb_ctx* c) {
+    if (!c->persist || !c->dev_rr) return false;
+    return (c->persist_v == 5 && c->jds_vec && c->pipe) || (c->persist_v == 4 && c->small_v2);
+}
 
 void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_warm) {
     const int n = c->n;
     const int k_lim = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps, n - 1));
     const double* src = (use_warm && c->have_prev_v) ? c->d_v : c->d_x0;
-    launch_spmv<0>(c, src, c->d_y);   // z_0 = L u_0 (the shift is applied by the init kernel)
-    k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1], c->d_basis,
-                                                              c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst, c->d_alpha,
-                                                              c->d_beta, k_lim + 2, c->d_rr_out, c->d_dev_stop);
+    const bool small = c->persist_v == 4;
+    if (small) {
+        k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs, 2 * c->p_ncta,
+                                                                     nullptr, nullptr, 0);
+        k_rr_reset<<<c->grid_for(k_lim + 2), kBlock, 0, c->stream>>>(c->d_alpha, c->d_beta, k_lim + 2, c->d_rr_out, c->d_dev_stop);
+    } else {
+        launch_spmv<0>(c, src, c->d_y);   // z_0 = L u_0 (the shift is applied by the init kernel)
+        k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1], c->d_basis,
+                                                                  c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst, c->d_alpha,
+                                                                  c->d_beta, k_lim + 2, c->d_rr_out, c->d_dev_stop);
+    }
     CK(cudaGetLastError());
     RrArgs R;
     R.alpha = c->d_alpha; R.beta = c->d_beta;
@@ -1154,7 +1192,8 @@ void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_war
     c->rr_launch = R;
     launch_persist(c, k_lim + 1, true);
     c->rr_launch.enabled = 0;
-    k_ritz<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->ld, 0, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(), c->d_jrow, c->d_rr_out);
+    k_ritz<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->ld, 0, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(), small ? nullptr : c->d_jrow,
+                                                        c->d_rr_out);
     k_center_normalize<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->d_v, c->d_sc);
     launch_spmv<2>(c, c->d_v, c->d_y);
     k_resid_l1<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->d_v, c->d_y, c->d_sc, c->ws());

@@ -1729,6 +1729,7 @@ struct RrArgs {
     const LzScalars* sc;   // sc->lnorm
     double tol;
     int n, k_limit, check_div, enabled;
+    int smem_doubles;      // dynamic shared memory of the launch, in doubles (the Rayleigh-Ritz CTA keeps T_k there)
 };
 
 struct LzPipeArgs {
@@ -2165,10 +2166,10 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
         double lo = gl - 2.0 * eps * tnorm * k - 2.0 * pivmin;
         double hi = fmin(gu + 2.0 * eps * tnorm * k + 2.0 * pivmin, amin + 4.0 * eps * tnorm);
         RR_STAGE(1);
-        // Once two consecutive checks agree on theta to 1e-8 it is no longer searched for: the eigenvector recurrences below
+        // Once two consecutive checks agree on theta to 2e-7 it is no longer searched for: the eigenvector recurrences below
         // tolerate that error (the tail of the vector moves by (k - i0) d(theta) / gap), and an accepted pair is polished by
         // its Rayleigh quotient.  Ritz values only decrease with k, by less every check.
-        const bool theta_frozen = theta_prev < inf && theta_delta >= 0.0 && theta_delta < 2e-8 * fabs(theta_prev) && !invariant;
+        const bool theta_frozen = theta_prev < inf && theta_delta >= 0.0 && theta_delta < 4e-7 * fabs(theta_prev) && !invariant;
         if (k == 1) {
             theta = in_s ? a_s[0] : R.a[0];
         } else if (theta_frozen) {
@@ -2195,14 +2196,14 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
                 }
             }
             // ---- multisection: kRrProbes interior shifts per round (more would be bound by the SM's 64 FP64 lanes, not by the
-            // latency of the recurrence), down to a relative width of 1e-9: the decision needs the residual estimate to ~10 %,
+            // latency of the recurrence), down to a relative width of 1e-7: the decision needs the residual estimate to ~10 %,
             // and the tail of the eigenvector moves by (k - i0) d(theta) / gap -- 1e-7 in theta would do
             constexpr int kRrProbes = 256;
             RR_STAGE(2);
             for (int round = 0; round < 40; ++round) {
                 ++rounds;
                 const double width = hi - lo;
-                if (!(width > 1e-9 * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
+                if (!(width > 1e-7 * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
                 bool neg = false;
                 if (tid < kRrProbes) {
                     const double x = lo + width * ((double)(tid + 1) / (double)(kRrProbes + 1));
@@ -2348,7 +2349,7 @@ template <bool SORTED, int VB>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P, RrArgs R) {
     if (blockIdx.x == (unsigned int)a.ncta) {   // the extra CTA of the launch: on-device Rayleigh-Ritz / stop decision
         extern __shared__ double rr_smem[];
-        lz_rr_main(R, rr_smem, J.prod_cap + J.prod_cap / 2);
+        lz_rr_main(R, rr_smem, R.smem_doubles);
         return;
     }
     extern __shared__ double prod[];
@@ -2779,8 +2780,12 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, c
 // warp redundantly (one shared-memory round instead of a second stage + barrier), the coefficient chain runs on all
 // threads.  Three CTA barriers per step instead of six.  State hand-over through the sector buffer is compatible with
 // k_lz_persist_init and with itself: (0, u_j, u_{j-1}, diag) with coefficients (0, 1, 0, 0).
-__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, const double* __restrict__ diag) {
+__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, const double* __restrict__ diag, RrArgs R) {
     extern __shared__ double smem_small[];
+    if (blockIdx.x == 1) {   // second CTA of the launch: on-device Rayleigh-Ritz / stop decision (see lz_rr_main)
+        lz_rr_main(R, smem_small, R.smem_doubles);
+        return;
+    }
     const int n = a.n;
     const int nnz = a.rp[n];
     double* __restrict__ uvec = smem_small;            // [n]   u_phase
@@ -2833,6 +2838,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, 
         // host stop flag: requested every 8th phase, looked at 7 phases later (a host-memory load takes microseconds)
         if (tid == 0 && a.stop && (it & 7) == 0)
             asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_probe) : "l"(a.stop));
+        // device-resident flag of the Rayleigh-Ritz CTA: requested every 4th phase, looked at 3 phases later
+        if (tid == 0 && R.enabled && (it & 3) == 0)
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop_probe) : "l"(R.dev_stop) : "memory");
         // ---- pass 1: products from the shared-memory vector
 #pragma unroll
         for (int j = 0; j < kSmallSlots; ++j) {
@@ -2870,6 +2878,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, 
             if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = rsum;
         }
         if (tid == 0 && a.stop && (it & 7) == 7) stop_small = stop_probe;
+        if (tid == 0 && R.enabled && (it & 3) == 3) stop_small = stop_probe;
         __syncthreads();
         // ---- every warp finishes the block sums itself, then the coefficient chain on every thread
         const double t4 = warp_sum4(sm[lane], sm[kPWarps + lane], sm[2 * kPWarps + lane], sm[3 * kPWarps + lane], lane);
@@ -2913,8 +2922,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small2(LzPersistArgs a, 
         a.st->k1 = 0.0; a.st->k2 = 1.0; a.st->k3 = 0.0; a.st->k4 = 0.0;
         a.st->beta_prev = beta_prev;
         a.st->usum_prev = usum_prev;
+        if (R.enabled) R.out->phases = phase;
     }
 }
+
 
 // sectors for phase 0: (0, src_i, 0, diag_i) with (k1,k2,k3,k4) = (0,1,0,0)  =>  u_0 = src
 __global__ void __launch_bounds__(kBlock) k_lz_persist_init(int n, const double* __restrict__ src,
@@ -3451,6 +3462,21 @@ __global__ void __launch_bounds__(1024, 1) k_l2_read(const double2* __restrict__
     }
     const double t = (a0 + a1) + (a2 + a3);
     if (t == 1.2345e-300) sink[0] = t;   // never true: keeps the loads alive
+}
+
+// coefficients not yet produced read as NaN; Rayleigh-Ritz state cleared (engines without an init kernel of their own for this)
+__global__ void __launch_bounds__(kBlock) k_rr_reset(double* __restrict__ alpha, double* __restrict__ beta, int ncoef, RrOut* rr_out, int* dev_stop) {
+    const double nan1 = __longlong_as_double(0x7ff8000000000001ll);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncoef; i += gridDim.x * blockDim.x) {
+        alpha[i] = nan1;
+        beta[i] = nan1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rr_out->status = 0; rr_out->k = 0; rr_out->checks = 0; rr_out->phases = 0;
+        rr_out->theta = 0.0; rr_out->est = 0.0; rr_out->target = 0.0;
+        rr_out->cyc_wait = 0; rr_out->cyc_compute = 0; rr_out->lag = 0; rr_out->rounds = 0;
+        *dev_stop = 0;
+    }
 }
 
 __global__ void k_clear_lp_scalars(LzScalars* sc) {
