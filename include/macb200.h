@@ -159,7 +159,7 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
 int macb_spmv_engine(macb_handle h, int engine);
 
 /* Name of the Lanczos kernel this handle launches (chosen from the graph's size at the first eigen-solve):
- * "k_lanczos_vec", "k_lanczos_jds", "k_lanczos_slots", "k_lanczos_small", "k_lanczos_persist" or "k_spmv+k_lanczos_b"
+ * "k_lanczos_pipe" (default), "k_lanczos_small2" (graphs that fit one SM), "k_lanczos_slots" (chunked fall-back) or "k_lanczos_persist"
  * (CUDA-graph engine); "" before the first solve.  The pointer stays valid for the life of the handle. */
 const char* macb_lanczos_kernel_name(macb_handle h);
 

@@ -406,7 +406,7 @@ def host_build_pattern(n, fi, fj, ci, cj):
 
 
 def host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots=True, bankfit=True):
-    """Host helper (no GPU): the jagged-diagonal layout of k_lanczos_vec / k_lanczos_jds for a given CTA partition
+    """Host helper (no GPU): the jagged-diagonal layout of k_lanczos_pipe for a given CTA partition
     `row_start` (len ncta + 1).  Returns (jrow, jlen, jcol, jeid, jd[ncta, stride])."""
     L = lib()
     rp, col, eid, row_start = _i32(rp), _i32(col), _i32(eid), _i32(row_start)

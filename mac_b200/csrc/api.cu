@@ -35,7 +35,7 @@ std::mutex g_l2_mutex;
 struct L2Pin { int refs = 0; size_t carve = 0; };
 std::map<int, L2Pin> g_l2_pins;
 
-constexpr int kGraphSteps = 32;            // Lanczos steps per captured CUDA graph
+constexpr int kGraphSteps = 32;            // granularity of the Lanczos basis capacity
 constexpr size_t kFlushBytes = 512u << 20; // > 126 MB L2
 
 struct CudaFail {
@@ -100,20 +100,16 @@ struct macb_ctx {
     // Lanczos
     double* d_basis = nullptr;
     int64_t basis_cap = 0;  // number of Lanczos steps the basis can hold (cap + 1 vectors)
-    double *d_alpha = nullptr, *d_beta = nullptr, *d_ysum = nullptr, *d_usum = nullptr, *d_coef = nullptr;
+    double *d_alpha = nullptr, *d_beta = nullptr, *d_coef = nullptr;
     LzScalars* d_sc = nullptr;
     double *h_alpha = nullptr, *h_beta = nullptr;  // pinned
     LzScalars* h_sc = nullptr;                     // pinned
-    cudaGraphExec_t lz_graph = nullptr;
     // persistent engine
-    bool persist = true;
-    bool persist_stream = false;
     int persist_v = 3;             // 3: slot-parallel kernel (k_lanczos_slots); 1: row-parallel (k_lanczos_persist)
     int *d_chunk_ptr = nullptr, *d_chunk_row = nullptr;
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
     bool jds_sorted = false;
-    bool small_v2 = true;          // k_lanczos_small2 (3 CTA barriers per step) instead of k_lanczos_small (6)
     // chunked jagged-diagonal SpMV (k_spmv_jds): built on demand by macb_spmv_engine(h, 1)
     int spmv_engine = 0;           // 0: k_spmv (CSR, W lanes per row), 1: k_spmv_jds
     int sj_nchunks = 0;
@@ -138,8 +134,6 @@ struct macb_ctx {
     bool sect_joint = false;       // d_sect[1] points into d_sect[0]'s allocation
     double* d_zprev = nullptr;     // z_{j-1} across launches of k_lanczos_pipe
     bool l2_pinned = false;        // this handle holds a reference on the device's persisting-L2 carve-out
-    bool jds_vec = false;          // k_lanczos_vec (materialised u_j, 8-byte gathers) instead of k_lanczos_jds (32-byte sectors)
-    bool async_rr = true;          // asynchronous host Rayleigh-Ritz (stop flag + streamed alpha/beta)
     double* h_ab = nullptr;        // host-mapped [2 * (cap + 2)]
     int* h_stop = nullptr;         // host-mapped stop flag (the Lanczos kernels sample it once per phase)
     int check_div = 8;             // Rayleigh-Ritz check interval = k / check_div (24 when the graph fills the GPU)
@@ -168,7 +162,6 @@ struct macb_ctx {
     unsigned int* d_sel2_hist = nullptr;       // two-pass top-k: global 15-bit histogram, state, candidate keys of the chosen bin
     Sel2State* d_sel2 = nullptr;
     unsigned long long* d_sel_cand = nullptr;
-    bool topk8 = false;
     double *d_tmp_m2 = nullptr, *d_tmp_m3 = nullptr;
     cudaGraphExec_t sel_graph = nullptr;
 
@@ -311,11 +304,10 @@ void free_all(macb_ctx* c) {
         }
         cudaGetLastError();
     }
-    if (c->lz_graph) cudaGraphExecDestroy(c->lz_graph);
     if (c->sel_graph) cudaGraphExecDestroy(c->sel_graph);
     void* dptrs[] = {c->d_rp, c->d_col, c->d_eid, c->d_val, c->d_diag, c->d_ew, c->d_ci, c->d_cj, c->d_kappa,
                      c->d_x, c->d_g, c->d_tmp_m, c->d_sel, c->d_v, c->d_y, c->d_x0, c->d_tmp_n, c->d_basis,
-                     c->d_alpha, c->d_beta, c->d_ysum, c->d_usum, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
+                     c->d_alpha, c->d_beta, c->d_coef, c->d_sc, c->d_partials, c->d_counter,
                      c->d_sel_state, c->d_sel_state2, c->d_tmp_m2, c->d_tmp_m3, c->d_blockcnt, c->d_flush, c->d_row_start, c->d_sect[0], c->sect_joint ? nullptr : c->d_sect[1], c->d_precs, c->d_chunk_ptr, c->d_chunk_row,
                      c->d_pst, c->d_ptiming, c->d_jrow, c->d_jlen, c->d_jcol, c->d_jeid, c->d_jd, c->d_jval, c->d_xrec, c->d_sj_chunk_row, c->d_sj_chunk_jd, c->d_sj_jd,
                      c->d_sj_perm, c->d_sj_len, c->d_sj_col, c->d_sj_eid, c->d_sj_chunk_slot, c->d_sj_word, c->d_sj_val, c->d_sj_col0, c->d_zprev, c->d_rr_a, c->d_rr_b, c->d_rr_b2, c->d_rr_binv, c->d_rr_s, c->d_rr_out, c->d_dev_stop, c->d_rr_w, c->d_sel2_hist, c->d_sel2, c->d_sel_cand};
@@ -418,9 +410,6 @@ void launch_spmv(macb_ctx* c, const double* x, double* y) {
     a.x = x;
     a.y = y;
     a.sc = c->d_sc;
-    a.alpha = c->d_alpha;
-    a.beta = c->d_beta;
-    a.ysum = c->d_ysum;
     a.ws = c->ws();
     if (MODE == 0 && c->spmv_engine == 1 && c->d_sj_val) {
         SpmvJdsArgs j{c->sj_nchunks, c->d_sj_chunk_row, c->d_sj_chunk_slot, c->d_sj_chunk_jd, c->d_sj_col0, c->d_sj_jd, c->d_sj_perm,
@@ -436,20 +425,10 @@ void launch_spmv(macb_ctx* c, const double* x, double* y) {
     CK(cudaGetLastError());
 }
 
-void launch_lanczos_step(macb_ctx* c) {
-    launch_spmv<1>(c, c->d_basis, c->d_y);
-    k_lanczos_b<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, c->d_basis, c->d_y, c->d_alpha, c->d_beta,
-                                                             c->d_ysum, c->d_usum, c->d_sc, c->ws());
-    CK(cudaGetLastError());
-}
-
 template <int W>
 void launch_persist_w(macb_ctx* c, LzPersistArgs& a) {
     void* params[] = {&a};
-    if (c->persist_stream)
-        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W, true>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
-    else
-        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W, false>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_lanczos_persist<W>, dim3(a.ncta), dim3(kPBlock), params, 0, c->stream));
 }
 
 // One cooperative launch = `nphases` fused Lanczos phases (kernels.cuh, k_lanczos_persist).
@@ -475,64 +454,37 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     a.stop = async ? c->h_stop : nullptr;
     if (c->bench_time_iters) CK(cudaEventRecord(c->lz0, c->stream));
     if (c->persist_v == 4) {
-        if (c->small_v2) {
-            RrArgs R = c->rr_launch;
-            R.smem_doubles = (int)(c->slots_smem / 8);
-            if (R.enabled) {
-                a.ab_host = nullptr;
-                a.stop = nullptr;
-            }
-            const double* dg = c->d_diag;
-            void* sparams[] = {&a, &dg, &R};
-            // cooperative: the solver CTA and the Rayleigh-Ritz CTA must be co-resident (the second stops the first)
-            CK(cudaLaunchCooperativeKernel((void*)k_lanczos_small2, dim3(R.enabled ? 2 : 1), dim3(kPBlock), sparams, c->slots_smem, c->stream));
-        } else {
-            k_lanczos_small<<<1, kPBlock, c->slots_smem, c->stream>>>(a, c->d_diag);
+        RrArgs R = c->rr_launch;
+        R.smem_doubles = (int)(c->slots_smem / 8);
+        if (R.enabled) {
+            a.ab_host = nullptr;
+            a.stop = nullptr;
         }
-        CK(cudaGetLastError());
+        const double* dg = c->d_diag;
+        void* sparams[] = {&a, &dg, &R};
+        // cooperative: the solver CTA and the Rayleigh-Ritz CTA must be co-resident (the second stops the first)
+        CK(cudaLaunchCooperativeKernel((void*)k_lanczos_small2, dim3(R.enabled ? 2 : 1), dim3(kPBlock), sparams, c->slots_smem, c->stream));
     } else if (c->persist_v == 5) {
         LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
                     c->d_diag, c->d_jrow};
-        void* params[] = {&a, &J};
-        void* fn = c->jds_sorted ? (void*)k_lanczos_jds<true> : (void*)k_lanczos_jds<false>;
-        if (c->jds_vec && c->pipe) {
-            LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
-            RrArgs R = c->rr_launch;
-            R.smem_doubles = (int)(c->pipe_smem / 8);
-            if (R.enabled) {   // device-side decision: nothing is streamed to, or polled from, the host
-                a.ab_host = nullptr;
-                a.stop = nullptr;
-            }
-            void* pparams[] = {&a, &J, &P, &R};
-            void* pf;
-            switch (c->vec_batch) {
-                case 3: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 3> : (void*)k_lanczos_pipe<false, 3>; break;
-                case 4: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 4> : (void*)k_lanczos_pipe<false, 4>; break;
-                case 6: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 6> : (void*)k_lanczos_pipe<false, 6>; break;
-                case 7: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 7> : (void*)k_lanczos_pipe<false, 7>; break;
-                case 8: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 8> : (void*)k_lanczos_pipe<false, 8>; break;
-                default: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 5> : (void*)k_lanczos_pipe<false, 5>; break;
-            }
-            CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta + (R.enabled ? 1 : 0)), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
-            if (c->bench_time_iters) CK(cudaEventRecord(c->lz1, c->stream));
-            c->c_launches += 1;
-            if (!async) {
-                c->c_spmv += nphases;
-                c->c_steps += nphases;
-            }
-            return;
+        LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
+        RrArgs R = c->rr_launch;
+        R.smem_doubles = (int)(c->pipe_smem / 8);
+        if (R.enabled) {   // device-side decision: nothing is streamed to, or polled from, the host
+            a.ab_host = nullptr;
+            a.stop = nullptr;
         }
-        if (c->jds_vec) {
-            switch (c->vec_batch) {
-                case 3: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 3> : (void*)k_lanczos_vec<false, 3>; break;
-                case 4: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 4> : (void*)k_lanczos_vec<false, 4>; break;
-                case 6: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 6> : (void*)k_lanczos_vec<false, 6>; break;
-                case 7: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 7> : (void*)k_lanczos_vec<false, 7>; break;
-                case 8: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 8> : (void*)k_lanczos_vec<false, 8>; break;
-                default: fn = c->jds_sorted ? (void*)k_lanczos_vec<true, 5> : (void*)k_lanczos_vec<false, 5>; break;
-            }
+        void* pparams[] = {&a, &J, &P, &R};
+        void* pf;
+        switch (c->vec_batch) {
+            case 3: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 3> : (void*)k_lanczos_pipe<false, 3>; break;
+            case 4: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 4> : (void*)k_lanczos_pipe<false, 4>; break;
+            case 6: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 6> : (void*)k_lanczos_pipe<false, 6>; break;
+            case 7: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 7> : (void*)k_lanczos_pipe<false, 7>; break;
+            case 8: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 8> : (void*)k_lanczos_pipe<false, 8>; break;
+            default: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 5> : (void*)k_lanczos_pipe<false, 5>; break;
         }
-        CK(cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kPBlock), params, c->slots_smem, c->stream));
+        CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta + (R.enabled ? 1 : 0)), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
     } else if (c->persist_v == 3) {
         LzChunkArgs ch{c->d_chunk_ptr, c->d_chunk_row, c->slots_cache_cols, c->slots_prod_cap};
         void* params[] = {&a, &ch};
@@ -548,7 +500,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     }
 }
 
-// Jagged-diagonal layout of the Lanczos kernels k_lanczos_jds / k_lanczos_vec (pure host code, also exported as
+// Jagged-diagonal layout of the Lanczos kernel k_lanczos_pipe (pure host code, also exported as
 // macb_host_build_jds for the CPU test-suite).  CTA b owns the rows row_start[b] .. row_start[b+1] and their slots
 // rp[row_start[b]] .. rp[row_start[b+1]].  Inside a CTA the rows are renumbered by decreasing length ("engine numbering",
 // jrow[engine row] = caller row, jlen = its length) so that diagonal d -- the d-th slot of every row that has one -- is the
@@ -648,7 +600,7 @@ void alloc_device_rr(macb_ctx* c) {
     c->d_rr_b2 = dalloc<double>(cap2);
     c->d_rr_binv = dalloc<double>(cap2);
     c->d_rr_s = dalloc<double>(cap2);
-    c->d_rr_w = dalloc<double>(4 * cap2);
+    c->d_rr_w = dalloc<double>(2 * cap2);
     c->d_rr_out = dalloc<RrOut>(1);
     c->d_dev_stop = dalloc<int>(1);
     CK(cudaMallocHost(&c->h_rr, sizeof(RrOut)));
@@ -662,19 +614,15 @@ size_t rr_smem_bytes(const macb_ctx* c) {
 void setup_persist(macb_ctx* c) {
     const int n = c->n, W = c->W;
     std::vector<int> rs;
-    // small graphs: the whole Lanczos state in one SM's shared memory (k_lanczos_small)
+    // small graphs: the whole Lanczos state in one SM's shared memory (k_lanczos_small2)
     const size_t small_bytes = (size_t)32 * n + (size_t)16 * c->nnz;
     if (c->persist_v == 3 && small_bytes <= (size_t)224 * 1024 && c->nnz <= (int64_t)kSmallSlots * kPBlock &&
         n <= kSmallRows * kPBlock && !getenv("MACB_NO_SMALL")) {
         c->persist_v = 4;
         c->p_ncta = 1;
         c->slots_smem = small_bytes;
-        c->small_v2 = !getenv("MACB_SMALL_V1");
-        if (c->small_v2) {
-            alloc_device_rr(c);
-            if (c->dev_rr) c->slots_smem = std::max(small_bytes, rr_smem_bytes(c));
-        }
-        raise_dyn_smem((const void*)k_lanczos_small, (size_t)(small_bytes));
+        alloc_device_rr(c);
+        if (c->dev_rr) c->slots_smem = std::max(small_bytes, rr_smem_bytes(c));
         raise_dyn_smem((const void*)k_lanczos_small2, c->slots_smem);
         rs.assign(2, n);
         rs[0] = 0;
@@ -734,10 +682,13 @@ void setup_persist(macb_ctx* c) {
                 c->slots_smem = (size_t)max_slots * 12;
             }
             raise_dyn_smem((const void*)k_lanczos_slots, (size_t)(c->slots_smem));
-            // jagged-diagonal staging (k_lanczos_jds): one chunk per CTA, products + column cache + diagonal starts fit
+            // jagged-diagonal layout of k_lanczos_pipe: one chunk per CTA, products + column cache + diagonal starts fit, and the
+            // last ceil(ncta / 32) warps of every CTA free of rows (they poll the exchange records)
+            bool pipe_ok = !getenv("MACB_NO_PIPE") && c->p_ncta <= 256;
+            for (int b = 0; b < c->p_ncta && pipe_ok; ++b) pipe_ok = rs[b + 1] - rs[b] <= (kPWarps - (c->p_ncta + 31) / 32) * 32;
             const int64_t cap4 = std::max<int64_t>((max_slots + 3) / 4 * 4, kPBlock);   // >= kPBlock: prod[0 + tid] is always addressable
-            const int64_t stride = (maxrow + 8 + 3) / 4 * 4;   // + 8: k_lanczos_vec reads the diagonal starts eight at a time
-            if (single && c->slots_cache_cols && (size_t)cap4 * 12 + (size_t)stride * 4 <= (size_t)224 * 1024 && !getenv("MACB_NO_JDS") &&
+            const int64_t stride = (maxrow + 8 + 3) / 4 * 4;   // + 8: the row sums read the diagonal starts eight at a time
+            if (pipe_ok && single && c->slots_cache_cols && (size_t)cap4 * 12 + (size_t)stride * 4 <= (size_t)224 * 1024 && !getenv("MACB_NO_JDS") &&
                 !c->h_col.empty()) {
                 const int ncta = c->p_ncta;
                 std::vector<int> jrow((size_t)n), jlen((size_t)n), jcol((size_t)c->nnz), jeid((size_t)c->nnz),
@@ -762,22 +713,8 @@ void setup_persist(macb_ctx* c) {
                 c->jd_stride = (int)stride;
                 c->slots_prod_cap = (int)cap4;
                 c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
-                                c->pipe_smem = c->slots_smem;
-                {   // k_lanczos_pipe wants its last ceil(ncta / 32) warps free of rows (they poll the exchange records)
-                    int maxrows = 0;
-                    for (int b = 0; b < ncta; ++b) maxrows = std::max(maxrows, rs[b + 1] - rs[b]);
-                    c->pipe = !getenv("MACB_NO_PIPE") && ncta <= 256 && maxrows <= (kPWarps - (ncta + 31) / 32) * 32;
-                }
-                raise_dyn_smem((const void*)k_lanczos_jds<false>, (size_t)(c->slots_smem));
-                raise_dyn_smem((const void*)k_lanczos_jds<true>, (size_t)(c->slots_smem));
-#define MACB_VEC_SMEM(VB_)                                                                                                                   \
-    raise_dyn_smem((const void*)k_lanczos_vec<false, VB_>, c->slots_smem); \
-    raise_dyn_smem((const void*)k_lanczos_vec<true, VB_>, c->slots_smem);  \
-    if (c->pipe) {                                                                                                                        \
-        raise_dyn_smem((const void*)k_lanczos_pipe<false, VB_>, c->pipe_smem); \
-        raise_dyn_smem((const void*)k_lanczos_pipe<true, VB_>, c->pipe_smem);  \
-    }
-                MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
+                c->pipe_smem = c->slots_smem;
+                c->pipe = true;
                 {   // gathers in flight per thread: the batch size whose last batch of a step is fullest (see kernels.cuh)
                     const double pt = (double)max_slots / (double)kPBlock;
                     double best = -1.0;
@@ -794,14 +731,15 @@ void setup_persist(macb_ctx* c) {
                         if (vb >= 3 && vb <= 8) c->vec_batch = vb;
                     }
                 }
-                c->jds_vec = !getenv("MACB_NO_VEC");
                 c->d_zprev = dalloc<double>((size_t)n);
-                if (c->pipe) {
-                    alloc_device_rr(c);
-                    // the Rayleigh-Ritz CTA keeps T_k (seven arrays) in the launch's dynamic shared memory while it fits
-                    c->pipe_smem = std::max(c->pipe_smem, rr_smem_bytes(c));
-                    MACB_VEC_SMEM(3) MACB_VEC_SMEM(4) MACB_VEC_SMEM(5) MACB_VEC_SMEM(6) MACB_VEC_SMEM(7) MACB_VEC_SMEM(8)
-                }
+                alloc_device_rr(c);
+                // the Rayleigh-Ritz CTA keeps T_k (seven arrays) in the launch's dynamic shared memory while it fits
+                if (c->dev_rr) c->pipe_smem = std::max(c->pipe_smem, rr_smem_bytes(c));
+#define MACB_PIPE_SMEM(VB_)                                                \
+    raise_dyn_smem((const void*)k_lanczos_pipe<false, VB_>, c->pipe_smem); \
+    raise_dyn_smem((const void*)k_lanczos_pipe<true, VB_>, c->pipe_smem);
+                MACB_PIPE_SMEM(3) MACB_PIPE_SMEM(4) MACB_PIPE_SMEM(5) MACB_PIPE_SMEM(6) MACB_PIPE_SMEM(7) MACB_PIPE_SMEM(8)
+#undef MACB_PIPE_SMEM
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {
                     // keep the weights the Lanczos kernel streams every step (8 bytes per slot) in the persisting part of L2
@@ -869,7 +807,7 @@ void setup_persist(macb_ctx* c) {
     c->d_row_start = dalloc<int>(c->p_ncta + 1);
     CK(cudaMemcpyAsync(c->d_row_start, rs.data(), sizeof(int) * (c->p_ncta + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->persist_v == 5 && c->jds_vec && c->pipe) {
+    if (c->persist_v == 5) {
         // k_lanczos_pipe: one block of five rows of ld doubles (z buffers, u buffers, diagonal); see the kernel
         c->d_sect[0] = dalloc<double>((size_t)c->ld * 5);
         c->d_sect[1] = c->d_sect[0] + c->ld;
@@ -906,37 +844,13 @@ void ensure_basis(macb_ctx* c, int max_steps) {
     int64_t cap = std::max<int64_t>(2 * kGraphSteps, std::min<int64_t>(std::min<int64_t>(want, by_mem), 65536));
     cap = ((cap + kGraphSteps - 1) / kGraphSteps) * kGraphSteps;
     c->basis_cap = cap;
-    c->d_basis = dalloc<double>((size_t)(cap + 2) * c->ld);   // k_lanczos_vec writes u_{j+1} at the end of phase j
+    c->d_basis = dalloc<double>((size_t)(cap + 2) * c->ld);   // the kernels write u_{j+1} at the end of phase j
     c->d_alpha = dalloc<double>(cap + 1);
     c->d_beta = dalloc<double>(cap + 2);
-    c->d_ysum = dalloc<double>(cap + 1);
-    c->d_usum = dalloc<double>(cap + 2);
     c->d_coef = dalloc<double>(cap + 1);
     CK(cudaMallocHost(&c->h_alpha, sizeof(double) * (cap + 1)));
     CK(cudaMallocHost(&c->h_beta, sizeof(double) * (cap + 2)));
-    if (c->persist) {
-        setup_persist(c);
-        return;
-    }
-    // capture kGraphSteps Lanczos steps (2 kernels each) into one graph
-    cudaGraph_t g = nullptr;
-    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    for (int s = 0; s < kGraphSteps; ++s) launch_lanczos_step(c);
-    CK(cudaStreamEndCapture(c->stream, &g));
-    CK(cudaGraphInstantiate(&c->lz_graph, g, 0));
-    CK(cudaGraphDestroy(g));
-}
-
-void run_lanczos_steps(macb_ctx* c, int nsteps) {
-    int done = 0;
-    while (nsteps - done >= kGraphSteps) {
-        CK(cudaGraphLaunch(c->lz_graph, c->stream));
-        done += kGraphSteps;
-    }
-    for (; done < nsteps; ++done) launch_lanczos_step(c);
-    c->c_launches += 2 * (int64_t)nsteps;
-    c->c_spmv += nsteps;
-    c->c_steps += nsteps;
+    setup_persist(c);
 }
 
 struct FiedlerResult {
@@ -1160,8 +1074,7 @@ int lanczos_cycle_async(macb_ctx* c, double tol, int k_limit, double brk, int& t
 // -> normalisation -> Rayleigh quotient and the reference's residual (nx:243).  The caller synchronises when IT needs the
 // numbers (macb_fw_run: once per Frank-Wolfe iteration) and then calls finish_fiedler_device.
 bool device_fiedler_available(const macb_ctx* c) {
-    if (!c->persist || !c->dev_rr) return false;
-    return (c->persist_v == 5 && c->jds_vec && c->pipe) || (c->persist_v == 4 && c->small_v2);
+    return c->dev_rr && (c->persist_v == 5 || c->persist_v == 4);
 }
 
 void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_warm) {
@@ -1185,7 +1098,7 @@ void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_war
     R.a = c->d_rr_a; R.b = c->d_rr_b; R.b2 = c->d_rr_b2; R.binv = c->d_rr_binv; R.s = c->d_rr_s;
     {
         const size_t cap2 = (size_t)c->basis_cap + 4;
-        R.dp = c->d_rr_w; R.dm = c->d_rr_w + cap2; R.lp = c->d_rr_w + 2 * cap2; R.um = c->d_rr_w + 3 * cap2;
+        R.dp = c->d_rr_w; R.dm = c->d_rr_w + cap2;
     }
     R.coef = c->d_coef; R.out = c->d_rr_out; R.dev_stop = c->d_dev_stop; R.sc = c->d_sc;
     R.tol = tol; R.n = n; R.k_limit = k_lim; R.check_div = c->check_div; R.enabled = 1;
@@ -1268,129 +1181,28 @@ int run_fiedler(macb_ctx* c, double tol, int max_steps, int warm, FiedlerResult&
     for (int restart = 0; restart < 64; ++restart) {
         // ---- (re)start
         const double* src = use_warm ? c->d_v : c->d_x0;
-        if (c->persist && c->persist_v == 5 && c->jds_vec && c->pipe) {
+        if (c->persist_v == 5) {
             launch_spmv<0>(c, src, c->d_y);   // z_0 = L u_0 (the shift is applied by the init kernel)
             c->c_launches++;
             c->c_spmv++;
             k_lz_pipe_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_y, c->d_jrow, c->d_sc, c->d_sect[0], c->d_sect[1],
                                                                       c->d_basis, c->d_xrec, (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst,
                                                                       c->d_alpha, c->d_beta, 0, nullptr, nullptr);
-        } else if (c->persist && c->persist_v == 5 && c->jds_vec) {
-            k_lz_vec_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_jrow, c->d_sect[0], c->d_sect[1], c->d_xrec,
-                                                                     (int64_t)8 * c->p_ncta * c->p_ncta, c->d_pst);
-        } else if (c->persist) {
-            k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs,
-                                                                         2 * c->p_ncta, c->persist_v == 5 ? c->d_jrow : nullptr, c->d_xrec,
-                                                                         c->d_xrec ? (int64_t)8 * c->p_ncta * c->p_ncta : 0);
         } else {
-            CK(cudaMemcpyAsync(c->d_basis, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-            k_set_lanczos_start<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_beta, c->d_usum, use_warm ? 1.0 : c->x0_norm);
-            c->h_beta[0] = use_warm ? 1.0 : c->x0_norm;
+            k_lz_persist_init<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, src, c->d_diag, c->d_sect[0], c->d_pst, c->d_precs,
+                                                                         2 * c->p_ncta, nullptr, nullptr, 0);
         }
         CK(cudaGetLastError());
         c->c_launches++;
-        if (c->persist && c->async_rr) {
+        {
             const int k_lim = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
             const int rc = lanczos_cycle_async(c, tol, k_lim, brk, total_steps, s, out);
             out.steps = total_steps;
             c->have_v = true;
             if (rc == 1) return MACB_OK;
-            use_warm = true;
+            use_warm = true;   // explicit restart from the current Ritz vector
             if (rc < 0 || total_steps >= max_steps) break;
-            continue;
         }
-        int k_done = 0;      // size of the usable tridiagonal T_k (needs beta[0..k])
-        int k_a = 0, k_b = 0;            // last two convergence checks: (k, residual estimate)
-        double est_a = 0.0, est_b = 0.0, theta_delta = -1.0;
-        bool resid_miss = false;
-        int phases = 0;      // persistent engine: phases run (phase j yields alpha[j], beta[j]) => k_done = phases - 1
-        double theta_prev = std::numeric_limits<double>::infinity();
-        // at most n - 1 steps per cycle: the Krylov space on 1-perp is exhausted by then, and a cycle
-        // that long without convergence is restarted from its Ritz vector below.
-        const int k_limit = (int)std::min<int64_t>(c->basis_cap, (int64_t)std::min(max_steps - total_steps, n - 1));
-        bool invariant = false;
-        while (true) {
-            // Batch size: the residual estimate of the smallest Ritz pair decays geometrically once the pair is
-            // resolved, so two checks predict where it will cross the tolerance.  Every check costs a host round
-            // trip plus a tridiagonal eigen-solve, so fewer is better.  The schedule depends only on this solve's
-            // own data (no cross-solve history), which keeps a solve a pure function of (L(x), start vector).
-            int batch;
-            if (k_done == 0) {
-                batch = kGraphSteps;
-            } else {
-                batch = (k_done < 4 * kGraphSteps) ? kGraphSteps
-                                                   : std::min(16 * kGraphSteps, ((k_done / 4) / kGraphSteps) * kGraphSteps);
-                if (resid_miss) {
-                    batch = std::max(8, k_done / 16);
-                } else if (k_b > k_a && est_a > 0.0 && est_b > 0.0) {
-                    const double slope = (std::log(est_b) - std::log(est_a)) / (double)(k_b - k_a);
-                    const double target = 0.5 * tol * lnorm / sqrtn;
-                    if (slope < -1e-4 && est_b > target) {
-                        const double pred = (std::log(target) - std::log(est_b)) / slope;
-                        batch = (int)std::min<double>(std::max(8.0, std::ceil(1.05 * pred) + 2.0), (double)std::max(kGraphSteps, k_done));
-                    }
-                }
-            }
-            batch = std::min(batch, k_limit - k_done);
-            if (batch > 0) {
-                if (c->persist) {
-                    const int run = batch + (phases == 0 ? 1 : 0);
-                    launch_persist(c, run);
-                    CK(cudaMemcpyAsync(c->h_alpha + phases, c->d_alpha + phases, sizeof(double) * run, cudaMemcpyDeviceToHost,
-                                       c->stream));
-                    CK(cudaMemcpyAsync(c->h_beta + phases, c->d_beta + phases, sizeof(double) * run, cudaMemcpyDeviceToHost,
-                                       c->stream));
-                    phases += run;
-                } else {
-                    run_lanczos_steps(c, batch);
-                    CK(cudaMemcpyAsync(c->h_alpha + k_done, c->d_alpha + k_done, sizeof(double) * batch, cudaMemcpyDeviceToHost,
-                                       c->stream));
-                    CK(cudaMemcpyAsync(c->h_beta + k_done + 1, c->d_beta + k_done + 1, sizeof(double) * batch,
-                                       cudaMemcpyDeviceToHost, c->stream));
-                }
-                CK(cudaStreamSynchronize(c->stream));
-                k_done += batch;
-                total_steps += batch;
-            }
-            // breakdown: beta[j] ~ 0 => span(u_0..u_{j-1}) is invariant and T_j is exact
-            int k = k_done;
-            for (int j = 1; j <= k_done; ++j)
-                if (!(c->h_beta[j] > brk)) {
-                    k = j;
-                    invariant = true;
-                    break;
-                }
-            if (k == 0) throw ArgFail{"macb_fiedler: Lanczos made no progress", MACB_ERR_STATE};
-            const double theta = tridiag_smallest_value(c->h_alpha, c->h_beta, k,
-                                                        invariant ? std::numeric_limits<double>::infinity() : theta_prev,
-                                                        theta_delta);
-            s.resize(k);
-            tridiag_vector(c->h_alpha, c->h_beta, k, theta, s.data());
-            if (std::isfinite(theta_prev)) theta_delta = 2.0 * std::fabs(theta_prev - theta);
-            theta_prev = theta;
-            const double est = std::fabs(c->h_beta[k]) * std::fabs(s[k - 1]);
-            k_a = k_b;
-            est_a = est_b;
-            k_b = k;
-            est_b = est;
-            resid_miss = false;
-            const bool exhausted = invariant || k_done >= k_limit;
-            if (est * sqrtn < tol * lnorm || exhausted) {
-                finalize_ritz(c, k, s, out);
-                out.steps = total_steps;
-                if (out.resid < tol) {
-                    out.converged = true;
-                    c->have_v = true;
-                    return MACB_OK;
-                }
-                resid_miss = true;
-                if (exhausted) break;  // restart from the best Ritz vector (now in d_v)
-            }
-        }
-        c->have_v = true;
-        use_warm = true;  // explicit restart from the current Ritz vector
-        if (total_steps >= max_steps) break;
-        if (invariant) break;  // T_k was exact and still missed tol: tol is below what double precision resolves
     }
     out.steps = total_steps;
     return MACB_NOT_CONVERGED;
@@ -1429,13 +1241,7 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
     const int grid = c->grid_for(m);
     k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
     c->c_launches++;
-    if (k > 0 && c->topk8) {   // MACB_TOPK8=1: the eight-pass radix select (kept for A/B)
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            k_sel_hist<<<grid, kBlock, 0, c->stream>>>(m, g, st, shift);
-            k_sel_pick<<<1, kBlock, 0, c->stream>>>(st, shift);
-        }
-        c->c_launches += 16;
-    } else if (k > 0 && m <= kSel2SmallMax) {
+    if (k > 0 && m <= kSel2SmallMax) {
         k_sel2_small<<<1, kSel2Block, kSel2Bins * sizeof(unsigned int), c->stream>>>(m, g, (long long)k, st);
         c->c_launches += 1;
     } else if (k > 0) {
@@ -1609,9 +1415,6 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         c->h_rp = rp;
         c->h_col = col;
         c->h_eid = eid;
-        if (const char* env = getenv("MACB_LANCZOS")) c->persist = (std::string(env) != "graph");
-        if (const char* env = getenv("MACB_PERSIST_STREAM")) c->persist_stream = atoi(env) != 0;
-        if (const char* env = getenv("MACB_ASYNC")) c->async_rr = atoi(env) != 0;
         if (const char* env = getenv("MACB_PERSIST_V")) c->persist_v = atoi(env);
 
         c->d_rp = dalloc<int>(n + 1);
@@ -1643,7 +1446,6 @@ int macb_create(int32_t n, int64_t nf, const int32_t* fi, const int32_t* fj, con
         CK(cudaMemsetAsync(c->d_sel2, 0, sizeof(Sel2State), c->stream));
         raise_dyn_smem((const void*)k_sel2_hist, (size_t)(kSel2Bins * sizeof(unsigned int)));
         raise_dyn_smem((const void*)k_sel2_small, (size_t)(kSel2Bins * sizeof(unsigned int)));
-        c->topk8 = getenv("MACB_TOPK8") != nullptr;
         CK(cudaMallocHost(&c->h_sc, sizeof(LzScalars)));
         CK(cudaMallocHost(&c->h_sel_state, sizeof(SelState)));
         CK(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(unsigned int), c->stream));
@@ -2077,7 +1879,7 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
         *algo_bytes_per_phase = h->lz_algo_bytes / (double)h->lz_kernel_phases;
     } else if (algo_bytes_per_phase) {
         const double spmv = (double)(h->nnz + h->n) * 12.0 + ((double)h->n + 1.0) * 4.0 + 16.0 * (double)h->n;
-        const bool vec = h->persist && h->persist_v == 5 && h->jds_vec;
+        const bool vec = h->persist_v == 5;
         *algo_bytes_per_phase = spmv + (vec ? 24.0 : 40.0) * (double)h->n;
     }
     return MACB_OK;
@@ -2085,10 +1887,9 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
 
 const char* macb_lanczos_kernel_name(macb_handle h) {
     if (!h || !h->d_basis) return "";
-    if (!h->persist) return "k_spmv+k_lanczos_b";
     switch (h->persist_v) {
-        case 5: return h->jds_vec ? (h->pipe ? "k_lanczos_pipe" : "k_lanczos_vec") : "k_lanczos_jds";
-        case 4: return h->small_v2 ? "k_lanczos_small2" : "k_lanczos_small";
+        case 5: return "k_lanczos_pipe";
+        case 4: return "k_lanczos_small2";
         case 3: return "k_lanczos_slots";
         default: return "k_lanczos_persist";
     }

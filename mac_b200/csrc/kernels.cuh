@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(kBlock) k_assemble(int n, const int* __restric
 
 // ---- K1: CSR SpMV, W lanes per row, fused reductions ---------------------------------------------
 // MODE 0: y = L x
-// MODE 1: Lanczos A-step: x = basis[j] / beta[j]; y = L x; alpha[j] = x.y; ysum[j] = sum y
 // MODE 2: Rayleigh: y = L x; vLv = x.y; vv = x.x
 struct SpmvArgs {
     int n;
@@ -204,12 +203,9 @@ struct SpmvArgs {
     const int* col;
     const double* val;
     const double* diag;
-    const double* x;     // MODE 0/2 input; MODE 1: basis base pointer
+    const double* x;
     double* y;
     LzScalars* sc;
-    double* alpha;       // MODE 1
-    const double* beta;  // MODE 1
-    double* ysum;        // MODE 1
     ReduceWS ws;
 };
 
@@ -224,13 +220,6 @@ __global__ void __launch_bounds__(kBlock) k_spmv(SpmvArgs a) {
     const int sub_in_warp = sub % rows_per_warp;
 
     const double* __restrict__ x = a.x;
-    double scale = 1.0;
-    int j = 0;
-    if (MODE == 1) {
-        j = a.sc->step;
-        x = a.x + (size_t)j * a.ld;
-        scale = safe_inv(a.beta[j]);
-    }
     const int* __restrict__ col = a.col;
     const double* __restrict__ val = a.val;
 
@@ -254,12 +243,9 @@ __global__ void __launch_bounds__(kBlock) k_spmv(SpmvArgs a) {
         for (int o = W / 2; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
         if (row < a.n && lane == 0) {
             const double xi = ld_nc(x + row);
-            const double yi = scale * (a.diag[row] * xi - acc0);
+            const double yi = a.diag[row] * xi - acc0;
             a.y[row] = yi;
-            if (MODE == 1) {
-                r0 = fma(xi * scale, yi, r0);
-                r1 += yi;
-            } else if (MODE == 2) {
+            if (MODE == 2) {
                 r0 = fma(xi, yi, r0);
                 r1 = fma(xi, xi, r1);
             }
@@ -268,13 +254,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv(SpmvArgs a) {
     if (MODE != 0) {
         double v[2] = {r0, r1};
         if (grid_reduce<2>(v, a.ws, sm, &flag)) {
-            if (MODE == 1) {
-                a.alpha[j] = v[0];
-                a.ysum[j] = v[1];
-            } else {
-                a.sc->vLv = v[0];
-                a.sc->vv = v[1];
-            }
+            a.sc->vLv = v[0];
+            a.sc->vv = v[1];
         }
     }
 }
@@ -383,46 +364,6 @@ __global__ void __launch_bounds__(kSjBlock, 4) k_spmv_jds(SpmvJdsArgs a) {
     }
 }
 
-// ---- K3: Lanczos B-step ---------------------------------------------------------------------------
-// u_{j+1} = y - alpha_j v_j - beta_j v_{j-1} - c 1 ;  beta_{j+1} = ||u_{j+1}|| ; step = j + 1
-// Three-term recurrence of the operator P L P, P = I - 11^T/n: the projection the reference applies
-// to its block at nx:206-210,251 is applied to every Lanczos vector here.  c is the mean of the WHOLE
-// right-hand side -- mean(y) minus the (rounding-level) means the stored u_j, u_{j-1} still carry,
-// which usum[] tracks -- not just mean(y): 0 lies outside the spectrum of P L P on 1-perp, so a
-// 1-component left to the recurrence alone grows like the Lanczos polynomial p_j(0) and the null
-// eigenvalue reappears in T_k after ~100 steps.
-__global__ void __launch_bounds__(kBlock) k_lanczos_b(int n, int ld, double* __restrict__ basis,
-                                                      const double* __restrict__ y, const double* __restrict__ alpha,
-                                                      double* __restrict__ beta, const double* __restrict__ ysum,
-                                                      double* __restrict__ usum, LzScalars* sc, ReduceWS ws) {
-    __shared__ double sm[2 * kWarpsPerBlock];
-    __shared__ int flag;
-    const int j = sc->step;
-    const double a = alpha[j];
-    const double bj = beta[j];
-    const double binv = safe_inv(bj);
-    const double bpinv = (j > 0) ? safe_inv(beta[j - 1]) : 0.0;
-    const double ca = a * binv;        // coefficient of u_j
-    const double cb = bj * bpinv;      // coefficient of u_{j-1}
-    const double c = (ysum[j] - ca * usum[j] - ((j > 0) ? cb * usum[j - 1] : 0.0)) / (double)n;
-    const double* __restrict__ uj = basis + (size_t)j * ld;
-    const double* __restrict__ up = basis + (size_t)(j > 0 ? j - 1 : 0) * ld;
-    double* __restrict__ un = basis + (size_t)(j + 1) * ld;
-    double acc = 0.0, sum = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double w = y[i] - ca * uj[i] - cb * up[i] - c;
-        un[i] = w;
-        acc = fma(w, w, acc);
-        sum += w;
-    }
-    double v[2] = {acc, sum};
-    if (grid_reduce<2>(v, ws, sm, &flag)) {
-        beta[j + 1] = sqrt(v[0]);
-        usum[j + 1] = v[1];
-        sc->step = j + 1;
-    }
-}
-
 // ---- K3 (persistent form): the whole Lanczos batch in ONE cooperative kernel -----------------------
 // State per node i is one 32-byte sector  S_i = (z_i, u_i, u'_i, diag_i)  with
 //     z = L u (un-normalised),  u = current Lanczos vector u_j,  u' = u_{j-1}.
@@ -513,17 +454,12 @@ __device__ __forceinline__ void ld_sector_if(const double* p, bool pred, double&
 constexpr int kPBlock = 1024;
 constexpr int kPWarps = kPBlock / 32;
 
-// STREAM = false: each sub-warp of W lanes walks its own row (W-strided segments of col/val).
-// STREAM = true : the warp reads the contiguous slot range of its rpw rows in fully coalesced 32-slot chunks
-//                 (4 chunks in flight), stages the products w_s * u_next[c_s] in shared memory, and the sub-warps
-//                 then sum their rows' segments from there ("CSR-stream" at warp granularity).  Same arithmetic,
-//                 ~3x fewer L1TEX wavefronts for the streamed (col, val) data.
-template <int W, bool STREAM>
+// Each sub-warp of W lanes walks its own row (W-strided segments of col/val).  The general fall-back: any row length, any size.
+template <int W>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a) {
     __shared__ double sm[4 * kPWarps];
     __shared__ double tot[4];
     __shared__ int stop_sm;
-    __shared__ double stage[STREAM ? kPWarps * 128 : 1];
     constexpr int rpw = 32 / W;                    // rows per warp per pass
     const int lane = threadIdx.x & (W - 1);
     const int sub = (threadIdx.x & 31) / W;
@@ -556,33 +492,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_persist(LzPersistArgs a)
             double acc0 = 0.0, acc1 = 0.0;
             double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;   // the row's own sector, requested before the gathers
             if (valid && lane == 0) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
-            if (STREAM) {
-                double* __restrict__ st = stage + warp * 128;
-                const int wl = threadIdx.x & 31;
-                const int rs = valid ? rp[row] : 0, re = valid ? rp[row + 1] : 0;
-                const int sA = rp[base], sB = rp[min(base + rpw, r1)];
-                for (int t0 = sA; t0 < sB; t0 += 128) {
-                    const int i0 = t0 + wl, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
-                    const bool v0 = i0 < sB, v1 = i1 < sB, v2 = i2 < sB, v3 = i3 < sB;
-                    const int c0 = v0 ? ld_nc(col + i0) : 0, c1 = v1 ? ld_nc(col + i1) : 0, c2 = v2 ? ld_nc(col + i2) : 0,
-                              c3 = v3 ? ld_nc(col + i3) : 0;
-                    const double w0 = v0 ? ld_nc(val + i0) : 0.0, w1 = v1 ? ld_nc(val + i1) : 0.0,
-                                 w2 = v2 ? ld_nc(val + i2) : 0.0, w3 = v3 ? ld_nc(val + i3) : 0.0;
-                    double z0, u0, q0, z1, u1, q1, z2, u2, q2, z3, u3, q3;
-                    ld_sector_if(S + 4 * (size_t)c0, w0 != 0.0, z0, u0, q0);
-                    ld_sector_if(S + 4 * (size_t)c1, w1 != 0.0, z1, u1, q1);
-                    ld_sector_if(S + 4 * (size_t)c2, w2 != 0.0, z2, u2, q2);
-                    ld_sector_if(S + 4 * (size_t)c3, w3 != 0.0, z3, u3, q3);
-                    st[wl] = w0 * fma(k1, z0, fma(k2, u0, k3 * q0));
-                    st[wl + 32] = w1 * fma(k1, z1, fma(k2, u1, k3 * q1));
-                    st[wl + 64] = w2 * fma(k1, z2, fma(k2, u2, k3 * q2));
-                    st[wl + 96] = w3 * fma(k1, z3, fma(k2, u3, k3 * q3));
-                    __syncwarp();
-                    const int lo = max(rs, t0) - t0, hi = min(re, t0 + 128) - t0;
-                    for (int i = lo + lane; i < hi; i += W) acc0 += st[i];
-                    __syncwarp();
-                }
-            } else if (valid) {
+            if (valid) {
                 const int s1 = rp[row + 1];
                 for (int s = rp[row] + lane; s < s1; s += 4 * W) {
                     // four slots per lane in flight; out-of-row slots re-read slot s (same line) with weight 0
@@ -978,7 +888,7 @@ struct LzJdsArgs {
     int jd_stride;
     int prod_cap;           // slots reserved for the product buffer; the column cache and jd follow
     double* xrec;           // [2][ncta][ncta][4] inboxes of the all-to-all barrier, NaN = empty (k_lz_persist_init)
-    const double* diag;     // [n] weighted degrees, caller numbering (k_lanczos_vec keeps its row's in a register)
+    const double* diag;     // [n] weighted degrees, caller numbering 
     const int* perm;        // [n] engine -> caller numbering
 };
 // Engine numbering: inside every CTA's row range the rows are renumbered by decreasing length (perm[new] = old), so
@@ -1012,597 +922,8 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
     return k;   // lane l holds the total of value 2 * (l >> 4) + ((l >> 3) & 1)
 }
 
-// SORTED: the CTA's slots are stored in column order (lanes of a warp then share 128-byte lines of the sector array,
-// which is what the L1TEX stage charges for) and every slot carries the position of its product in the jagged
-// diagonal buffer: scol = column (17 bits) | position (14 bits) << 17 | inactive << 31.
-template <bool SORTED>
-__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_jds(LzPersistArgs a, LzJdsArgs J) {
-    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
-#define MACB_DST(cc, jj) (SORTED ? (((cc) >> 17) & 0x3fff) : (jj))
-    extern __shared__ double prod[];
-    __shared__ double sm[4 * kPWarps];
-    __shared__ double tot[4];
-    __shared__ int stop_sm;
-    __shared__ int stop_in;
-    __shared__ double carry[2][2];   // [parity][1/beta, sum(u)] of the last completed phase (kept out of registers)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
-    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
-    int* __restrict__ sjd = scol + J.prod_cap;
-    const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
-    const int sa = a.rp[ra], ns = a.rp[rb] - sa;
-    const bool has_row = tid < rb - ra;
-    const int row = ra + tid;
-    const int len = has_row ? J.jlen[row] : 0;
-    const double* __restrict__ jval = J.jval + sa;
-    for (int i = tid; i < ns; i += kPBlock)
-        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
-    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
-
-    int phase = a.st->phase;
-    int cur = a.st->cur;
-    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
-    if (tid == 0) {
-        carry[phase & 1][0] = a.st->beta_prev;   // 1/beta of the last completed step (slot of the NEXT phase's parity)
-        carry[phase & 1][1] = a.st->usum_prev;
-    }
-    __syncthreads();
-    const unsigned int ncta = (unsigned int)a.ncta;
-    const int j1 = tid + kPBlock, j2 = tid + 2 * kPBlock;
-    // early gathers per thread: slots per thread mod 4 (2 when that is 0)
-    const int per_thread = (ns + kPBlock - 1) / kPBlock;
-    const int E = (per_thread & 3) ? (per_thread & 3) : 2;
-    const double* const S0 = a.sect[0];
-    const double* const S1 = a.sect[1];
-    const double inv_n = 1.0 / (double)a.n;
-    const int rows_warps = (rb - ra + 31) >> 5;   // warps that own rows
-
-    for (int it = 0;; ++it) {
-        const bool more = it < a.nphases;
-        const double* __restrict__ S = cur ? S1 : S0;
-#ifdef MACB_PTIMING
-        long long t_start = clock64(), t_p1 = 0, t_coef = 0;
-#endif
-        // ---- totals of the phase that has just passed its barrier (shared memory), read BEFORE this thread's gathers
-        // enter the SM's memory pipe; the coefficient chain itself (one rsqrt + multiplications) runs after the
-        // first gathers have been issued and overlaps with their latency
-        double P1 = 0.0, P2 = 0.0, P3 = 0.0, P4 = 0.0, bprev = 0.0, uprev = 0.0;
-        int stop_all = 0;
-        if (it > 0) {
-            P1 = tot[0]; P2 = tot[1]; P3 = tot[2]; P4 = tot[3];
-            stop_all = stop_sm;
-            bprev = carry[(phase - 1) & 1][0];
-            uprev = carry[(phase - 1) & 1][1];
-        }
-        // ---- first E gathers of phase `phase` (they need addresses only); E = (slots per thread) mod 4 so that the
-        // main loop below runs full batches of four
-        double z0 = 0.0, u0 = 0.0, g0 = 0.0, z1 = 0.0, u1 = 0.0, g1 = 0.0, z2 = 0.0, u2 = 0.0, g2 = 0.0;
-        int c0 = (int)0x80000000, c1 = (int)0x80000000, c2 = (int)0x80000000;
-        int stop_now = 0;
-        if (more && !stop_all) {
-            // the stop flag lives in host-mapped memory (a PCIe round trip): fetch it with cp.async so that its latency
-            // is not tied to the scoreboard slots of this warp's gathers; it is consumed at the end of the step
-            if (blockIdx.x == 0 && tid == 0 && a.stop)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(&stop_in)), "l"(a.stop) : "memory");
-            if (tid < ns) c0 = scol[tid];
-            if (E > 1 && j1 < ns) c1 = scol[j1];
-            if (E > 2 && j2 < ns) c2 = scol[j2];
-            ld_sector_if(S + 4 * (size_t)(c0 & CM), c0 >= 0, z0, u0, g0);
-            if (E > 1) ld_sector_if(S + 4 * (size_t)(c1 & CM), c1 >= 0, z1, u1, g1);
-            if (E > 2) ld_sector_if(S + 4 * (size_t)(c2 & CM), c2 >= 0, z2, u2, g2);
-        }
-        if (it > 0) {
-            const int done = phase - 1;
-            const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (done > 0) ? bprev : 0.0, uprev, inv_n);
-            k1 = cf.k1; k2 = cf.k2; k3 = cf.k3; k4 = cf.k4;
-            if (tid == 0) {
-                carry[phase & 1][0] = cf.binv;
-                carry[phase & 1][1] = P4;
-                if (blockIdx.x == 0) {
-                    a.alpha[done] = cf.alpha;
-                    a.beta[done] = cf.beta;
-                    if (a.ab_host)
-                        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)done), "d"(cf.alpha), "d"(cf.beta) : "memory");
-                }
-            }
-            if (stop_all) break;
-        }
-#ifdef MACB_PTIMING
-        t_coef = clock64();
-#endif
-        if (!more) break;
-        // ---- products: the early gathers, then the rest of the CTA's slots four at a time; the row's own sector is
-        // requested with the last batch (it is needed in pass 2 only)
-        double* __restrict__ D = cur ? a.sect[0] : a.sect[1];
-        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
-        double oz = 0.0, ou = 0.0, oq = 0.0, od = 0.0;
-        {
-            const double w0 = (c0 >= 0) ? ld_nc(jval + tid) : 0.0;
-            if (tid < ns) prod[MACB_DST(c0, tid)] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
-            if (E > 1) {
-                const double w1 = (c1 >= 0) ? ld_nc(jval + j1) : 0.0;
-                if (j1 < ns) prod[MACB_DST(c1, j1)] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
-            }
-            if (E > 2) {
-                const double w2 = (c2 >= 0) ? ld_nc(jval + j2) : 0.0;
-                if (j2 < ns) prod[MACB_DST(c2, j2)] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
-            }
-        }
-        bool own_pending = has_row;
-        for (int b0 = tid + E * kPBlock; b0 < ns; b0 += 4 * kPBlock) {
-            const int b1 = b0 + kPBlock, b2 = b0 + 2 * kPBlock, b3 = b0 + 3 * kPBlock;
-            const bool v1 = b1 < ns, v2 = b2 < ns, v3 = b3 < ns;
-            double z3, u3, g3;
-            c0 = scol[b0];
-            c1 = v1 ? scol[b1] : (int)0x80000000;
-            c2 = v2 ? scol[b2] : (int)0x80000000;
-            const int c3 = v3 ? scol[b3] : (int)0x80000000;
-            if (own_pending && b0 + 4 * kPBlock >= ns) {
-                ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);
-                own_pending = false;
-            }
-            ld_sector_if(S + 4 * (size_t)(c0 & CM), c0 >= 0, z0, u0, g0);
-            ld_sector_if(S + 4 * (size_t)(c1 & CM), c1 >= 0, z1, u1, g1);
-            ld_sector_if(S + 4 * (size_t)(c2 & CM), c2 >= 0, z2, u2, g2);
-            ld_sector_if(S + 4 * (size_t)(c3 & CM), c3 >= 0, z3, u3, g3);
-            const double w0 = (c0 >= 0) ? ld_nc(jval + b0) : 0.0, w1 = (c1 >= 0) ? ld_nc(jval + b1) : 0.0,
-                         w2 = (c2 >= 0) ? ld_nc(jval + b2) : 0.0, w3 = (c3 >= 0) ? ld_nc(jval + b3) : 0.0;
-            prod[MACB_DST(c0, b0)] = w0 * fma(k1, z0, fma(k2, u0, k3 * g0));
-            if (v1) prod[MACB_DST(c1, b1)] = w1 * fma(k1, z1, fma(k2, u1, k3 * g1));
-            if (v2) prod[MACB_DST(c2, b2)] = w2 * fma(k1, z2, fma(k2, u2, k3 * g2));
-            if (v3) prod[MACB_DST(c3, b3)] = w3 * fma(k1, z3, fma(k2, u3, k3 * g3));
-        }
-        if (own_pending) ld_sector(S + 4 * (size_t)row, oz, ou, oq, od);   // rows of a CTA whose loop this thread never entered
-        __syncthreads();
-#ifdef MACB_PTIMING
-        t_p1 = clock64();
-#endif
-        // ---- row sums along the jagged diagonals (conflict-free), new sector, basis entry, partial sums
-        if (warp < rows_warps) {
-            double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
-            if (has_row) {
-                const double* __restrict__ pt = prod + tid;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int d = 0;
-                for (; d + 4 <= len; d += 4) {
-                    const int4 o = *reinterpret_cast<const int4*>(sjd + d);
-                    a0 += pt[o.x];
-                    a1 += pt[o.y];
-                    a2 += pt[o.z];
-                    a3 += pt[o.w];
-                }
-                for (; d < len; ++d) a0 += pt[sjd[d]];
-                const double acc = (a0 + a1) + (a2 + a3);
-                const double t = fma(k1, oz, fma(k2, ou, k3 * oq));
-                const double un = t + k4;                  // u_phase[row]
-                const double zn = fma(od, t, -acc);        // (L u_phase)[row]; L 1 = 0 cancels k4
-                st_sector(D + 4 * (size_t)row, zn, un, ou, od);
-                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
-                p1 = un * zn;
-                p2 = zn;
-                p3 = un * un;
-                p4 = un;
-            }
-            const double r = warp_sum4(p1, p2, p3, p4, lane);
-            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
-        }
-        __syncthreads();
-#ifdef MACB_PTIMING
-        long long t_rows = clock64();
-#endif
-        // ---- grid barrier = all-to-all exchange of the CTAs' partial sums.  Every CTA pushes its 32-byte record into
-        // a slot of EVERY CTA's private inbox (after a gpu-scope fence, so its sectors are visible first) and polls
-        // its own inbox until all slots are valid (the inbox is NaN-filled between uses; NaN partial sums are
-        // replaced by +inf at the source).  No atomic, no shared hot line (all readers polling one counter and then
-        // fetching the same 148 records cost 2-6 k cycles of L2 serialisation per step), and the data needed after
-        // the barrier IS the barrier.  CTA 0's stop decision rides on the sign of its (non-negative) sum of squares.
-#ifdef MACB_PTIMING
-        long long tb0 = 0, tb1 = 0, tb2 = 0, tb3 = 0;
-#endif
-        if (warp == 0) {
-            const double x0 = (lane < rows_warps) ? sm[lane] : 0.0, x1 = (lane < rows_warps) ? sm[kPWarps + lane] : 0.0,
-                         x2 = (lane < rows_warps) ? sm[2 * kPWarps + lane] : 0.0, x3 = (lane < rows_warps) ? sm[3 * kPWarps + lane] : 0.0;
-            const double r = warp_sum4(x0, x1, x2, x3, lane);
-            double q0 = __shfl_sync(0xffffffffu, r, 0), q1 = __shfl_sync(0xffffffffu, r, 8),
-                   q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
-            const double inf = __longlong_as_double(0x7ff0000000000000ll);
-            q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
-            if (blockIdx.x == 0 && a.stop) {
-                if (lane == 0) {
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    stop_now = *(volatile int*)&stop_in;
-                }
-                if (__shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
-            }
-            double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
-#ifdef MACB_PTIMING
-            tb0 = clock64();
-#endif
-            __threadfence();
-#ifdef MACB_PTIMING
-            tb1 = clock64();
-#endif
-            for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
-            const double* const mine = box + (size_t)blockIdx.x * ncta * 4;
-            double y0, y1, y2, y3;
-            int stop_seen;
-            unsigned int spins = 0;
-            while (true) {
-                bool ok = true;
-                y0 = y1 = y2 = y3 = 0.0;
-                stop_seen = 0;
-                for (unsigned int b = lane; b < ncta; b += 32) {
-                    double r0, r1, r2, r3;
-                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                 : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
-                    ok = ok && (r0 == r0) && (r1 == r1) && (r2 == r2) && (r3 == r3);
-                    if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
-                    y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
-                }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > (1u << 22)) break;   // ~seconds: never hang the device on a lost CTA; the sums are then NaN
-            }
-            // (no acquire fence: the next step's gathers are .cg loads issued after this warp-uniform exit and the
-            //  __syncthreads below; the writers fenced before pushing, so the sectors are in L2 by now)
-#ifdef MACB_PTIMING
-            tb2 = clock64();
-#endif
-            const double t = warp_sum4(y0, y1, y2, y3, lane);
-            if ((lane & 7) == 0) tot[lane >> 3] = t;
-            if (lane == 0) stop_sm = stop_seen;
-            const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-            for (unsigned int b = lane; b < ncta; b += 32) st_sector(const_cast<double*>(mine) + (size_t)b * 4, nanv, nanv, nanv, nanv);
-#ifdef MACB_PTIMING
-            tb3 = clock64();
-#endif
-        }
-        __syncthreads();
-#ifdef MACB_PTIMING
-        if (tid == 0 && a.timing && it < 64) {
-            long long* e = a.timing + (size_t)64 * a.ncta * 5 + ((size_t)it * a.ncta + blockIdx.x) * 4;
-            e[0] = tb0; e[1] = tb1; e[2] = tb2; e[3] = tb3;
-            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
-            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = t_coef;
-            a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
-        }
-#endif
-        cur ^= 1;
-        ++phase;
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-        a.st->phase = phase;
-        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
-        a.st->cur = cur;
-        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
-        a.st->beta_prev = carry[phase & 1][0];
-        a.st->usum_prev = carry[phase & 1][1];
-    }
-}
-#undef MACB_DST
-
-// ---- K3, materialised-vector form of the jagged-diagonal kernel (default when it applies) ------------------------
-// What the L1TEX stage charges for a gather is the number of distinct 128-byte lines a warp instruction touches.  A
-// 32-byte sector per node puts 4 nodes in a line; a plain vector of doubles puts 16.  With the CTA's slots stored in
-// column order, 32 consecutive lanes then touch ~12 lines instead of ~24 (headline graph: 5.7 k instead of 11.2 k
-// wavefronts per CTA and step).  So this kernel keeps u_j itself in global memory (two buffers of n doubles) and pays
-// for it with a short local pass after the barrier:
-//   pass 1   prod[dest_s] = w_s * U[col_s]                      (8-byte gathers, 8 in flight per thread)
-//   pass 2   z_i = d_i u_i - sum_s prod;  partial sums (u.z, sum z, u.u, sum u)         (rows of this CTA)
-//   barrier  all-to-all exchange of the partial sums (as k_lanczos_jds)  ->  alpha_j, beta_j, k1..k4
-//   pass B   u_{j+1}[i] = k1 z_i + k2 u_j[i] + k3 u_{j-1}[i] + k4  for the CTA's own rows (z, u_j, u_{j-1} are in
-//            registers); written to the other buffer and to the basis; the buffer just read is poisoned with NaN
-// There is no second barrier: a consumer that gathers NaN from the new buffer (its producer has not written yet)
-// gathers again.  The poison store of phase j is ordered before the producer's record push of phase j+1 by the
-// release fence of the exchange, so no consumer can see a value older than the poison.
-__device__ __forceinline__ double ld_f64_if(const double* p, bool pred) {
-    double v;
-    // relaxed.gpu, not a weak .cg load: the retry loop below re-reads the same address until the producer's store
-    // arrives, and ptxas is free to hoist a WEAK load out of such a loop (it did)
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.relaxed.gpu.global.f64 %0, [%1];\n\t}"
-                 : "=d"(v) : "l"(p), "r"((int)pred) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(kBlock) k_lz_vec_init(int n, const double* __restrict__ src, const int* __restrict__ perm,
-                                                        double* __restrict__ u0, double* __restrict__ u1, double* __restrict__ xrec,
-                                                        int64_t nxrec, LzPersistState* st) {
-    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        u0[i] = src[perm[i]];
-        u1[i] = nanv;
-    }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxrec; i += (int64_t)gridDim.x * blockDim.x) xrec[i] = nanv;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st->phase = 0;
-        st->cur = 0;
-        st->k1 = 0.0; st->k2 = 1.0; st->k3 = 0.0; st->k4 = 0.0;
-        st->beta_prev = 0.0;
-        st->usum_prev = 0.0;
-        st->bar = 0u;
-    }
-}
-
-// Gathers in flight per thread (template parameter VB of k_lanczos_vec).  What matters is how full the LAST batch of a
-// step is: every batch costs a full memory round trip whether one slot or VB of them ride on it.  Measured at the
-// headline size (14.55 slots per thread), us per step: VB = 3: 9.77, 4: 10.15, 5: 9.75, 6: 10.75, 7: 11.12, 8: 10.67 (and
-// a few spills), 10: 11.7.  The host picks the VB in 3..8 whose last batch is fullest (one full batch when a thread has
-// at most 8 slots).
-#ifdef MACB_DEBUG_VEC
-__device__ int g_dbg_count = 0;
-__device__ int g_prog[256];
-#define MACB_PROG(stage) do { if (tid == 0) { g_prog[blockIdx.x] = phase * 10 + (stage); } } while (0)
-#else
-#define MACB_PROG(stage) do {} while (0)
-#endif
-
-template <bool SORTED, int VB>
-__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJdsArgs J) {
-    constexpr int kVecBatch = VB;
-    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
-#define MACB_DST(cc, jj) (SORTED ? (((cc) >> 17) & 0x3fff) : (jj))
-    extern __shared__ double prod[];
-    __shared__ double sm[4 * kPWarps];
-    __shared__ double tot[4];
-    __shared__ int stop_sm;
-    __shared__ int stop_in;
-    __shared__ int give_up;
-#ifdef MACB_PTIMING
-    __shared__ int dbg_retries;
-#endif
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
-    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
-    int* __restrict__ sjd = scol + J.prod_cap;
-    const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
-    const int sa = a.rp[ra], ns = a.rp[rb] - sa;
-    const bool has_row = tid < rb - ra;
-    const int row = ra + tid;
-    const int len = has_row ? J.jlen[row] : 0;
-    const double od = has_row ? J.diag[J.perm[row]] : 0.0;
-    const double* __restrict__ jval = J.jval + sa;
-    for (int i = tid; i < ns; i += kPBlock)
-        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
-    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
-    if (tid == 0) give_up = 0;
-#ifdef MACB_PTIMING
-    if (tid == 0) dbg_retries = 0;
-#endif
-
-    int phase = a.st->phase;
-    int cur = a.st->cur;
-    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed phase
-    double* const U0 = a.sect[0];
-    double* const U1 = a.sect[1];
-    // own rows: u_j and u_{j-1} live in registers for the whole launch
-    double su = 0.0, sq = 0.0;
-    if (has_row) {
-        su = __ldcg((cur ? U1 : U0) + row);
-        if (phase > 0) sq = __ldcg(a.basis + (size_t)(phase - 1) * a.ld + row);
-        else a.basis[row] = su;
-    }
-    __syncthreads();
-    const unsigned int ncta = (unsigned int)a.ncta;
-    const double inv_n = 1.0 / (double)a.n;
-    const int rows_warps = (rb - ra + 31) >> 5;
-    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-
-    for (int it = 0; it < a.nphases; ++it) {
-        const double* __restrict__ U = cur ? U1 : U0;
-        double* __restrict__ Un = cur ? U0 : U1;
-#ifdef MACB_PTIMING
-        long long t_start = clock64(), t_p1 = 0, t_coef = 0;
-#endif
-        if (blockIdx.x == 0 && tid == 0 && a.stop)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(&stop_in)), "l"(a.stop) : "memory");
-        MACB_PROG(1);
-        // ---- pass 1: products of the CTA's slots, kVecBatch gathers in flight per thread
-        for (int b0 = tid; b0 < ns; b0 += kVecBatch * kPBlock) {
-            int c[kVecBatch];
-            double v[kVecBatch];
-#pragma unroll
-            for (int q = 0; q < kVecBatch; ++q) {
-                const int b = b0 + q * kPBlock;
-                c[q] = (b < ns) ? scol[b] : (int)0x80000000;
-            }
-#pragma unroll
-            for (int q = 0; q < kVecBatch; ++q) v[q] = ld_f64_if(U + (c[q] & CM), c[q] >= 0);
-            // the weights of the whole batch are requested up front as well: loaded one by one next to their use they
-            // form a chain of kVecBatch dependent L2 latencies per batch
-            double wq[kVecBatch];
-#pragma unroll
-            for (int q = 0; q < kVecBatch; ++q) wq[q] = (c[q] >= 0) ? ld_stream(jval + b0 + q * kPBlock) : 0.0;
-#pragma unroll
-            for (int q = 0; q < kVecBatch; ++q) {
-                const int b = b0 + q * kPBlock;
-                if (c[q] >= 0) {
-                    const double w = wq[q];
-                    if (v[q] != v[q]) {   // producer has not written yet: gather again (bounded: never hang the device)
-#ifdef MACB_PTIMING
-                        atomicAdd(&dbg_retries, 1);
-#endif
-                        unsigned int tries = 0;
-                        do {
-                            v[q] = ld_f64_if(U + (c[q] & CM), true);
-                        } while (v[q] != v[q] && ++tries < (1u << 17));
-                        if (v[q] != v[q]) {
-                            give_up = 1;
-#ifdef MACB_DEBUG_VEC
-                            if (atomicAdd(&g_dbg_count, 1) < 3) {
-                                for (int z = 0; z < (int)gridDim.x; ++z) printf("[vec] prog cta %d = %d\n", z, *(volatile int*)&g_prog[z]);
-                            }
-                            if (atomicAdd(&g_dbg_count, 1) < 12)
-                                printf("[vec] t=%lld cta %d tid %d phase %d it %d: column %d of buffer %d still NaN\n", (long long)clock64(), (int)blockIdx.x, tid, phase, it, c[q] & CM, cur);
-#endif
-                        }
-                    }
-                    prod[MACB_DST(c[q], b)] = w * v[q];
-                } else if (b < ns) {
-                    prod[MACB_DST(c[q], b)] = 0.0;
-                }
-            }
-        }
-        __syncthreads();
-#ifdef MACB_PTIMING
-        t_p1 = clock64();
-#endif
-        MACB_PROG(2);
-        // ---- pass 2: row sums along the jagged diagonals, z_i, partial sums
-        // The release fence of the record exchange (it orders the CTA's pass-B stores of the previous phase -- vector
-        // entries and poison -- before the record this CTA is about to push) is executed here by the last warp, which
-        // has no rows unless the CTA has more than 992: it overlaps with the row sums instead of sitting on warp 0's
-        // critical path.  fence (warp 31) -> __syncthreads -> push (warp 0) is a release sequence through the barrier.
-        if (warp == kPWarps - 1) __threadfence();
-        double zr = 0.0;
-        if (warp < rows_warps) {
-            double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
-            if (has_row) {
-                // eight diagonals per trip, predicated instead of a scalar tail (jd is padded by 8 entries): the row sums
-                // are latency-bound (dependent shared-memory loads), not bandwidth-bound
-                const double* __restrict__ pt = prod + tid;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
-                for (int d = 0; d < len; d += 8) {
-                    const int4 o = *reinterpret_cast<const int4*>(sjd + d);
-                    const int4 p = *reinterpret_cast<const int4*>(sjd + d + 4);
-                    const int r = len - d;
-                    a0 += pt[o.x];
-                    a1 += (r > 1) ? pt[o.y] : 0.0;
-                    a2 += (r > 2) ? pt[o.z] : 0.0;
-                    a3 += (r > 3) ? pt[o.w] : 0.0;
-                    a4 += (r > 4) ? pt[p.x] : 0.0;
-                    a5 += (r > 5) ? pt[p.y] : 0.0;
-                    a6 += (r > 6) ? pt[p.z] : 0.0;
-                    a7 += (r > 7) ? pt[p.w] : 0.0;
-                }
-                zr = fma(od, su, -(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))));   // (L u_phase)[row]
-                p1 = su * zr;
-                p2 = zr;
-                p3 = su * su;
-                p4 = su;
-            }
-            const double r = warp_sum4(p1, p2, p3, p4, lane);
-            if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
-        }
-        __syncthreads();
-#ifdef MACB_PTIMING
-        long long t_rows = clock64();
-        long long tb0 = 0, tb1 = 0, tb2 = 0, tb3 = 0;
-#endif
-        MACB_PROG(3);
-        // ---- barrier: all-to-all exchange of the partial sums (see k_lanczos_jds)
-        if (warp == 0) {
-            const double x0 = (lane < rows_warps) ? sm[lane] : 0.0, x1 = (lane < rows_warps) ? sm[kPWarps + lane] : 0.0,
-                         x2 = (lane < rows_warps) ? sm[2 * kPWarps + lane] : 0.0, x3 = (lane < rows_warps) ? sm[3 * kPWarps + lane] : 0.0;
-            const double r = warp_sum4(x0, x1, x2, x3, lane);
-            double q0 = __shfl_sync(0xffffffffu, r, 0), q1 = __shfl_sync(0xffffffffu, r, 8),
-                   q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
-            const double inf = __longlong_as_double(0x7ff0000000000000ll);
-            q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
-            if (*(volatile int*)&give_up) q0 = inf;   // poison alpha: the host sees a non-finite value and reports it
-            if (blockIdx.x == 0 && a.stop) {
-                int stop_now = 0;
-                if (lane == 0) {
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    stop_now = *(volatile int*)&stop_in;
-                }
-                if (__shfl_sync(0xffffffffu, stop_now, 0)) q2 = -q2;
-            }
-            double* const box = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4;   // [reader][writer][4]
-#ifdef MACB_PTIMING
-            tb0 = clock64();
-            tb1 = tb0;
-#endif
-            for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
-            const double* const mine = box + (size_t)blockIdx.x * ncta * 4;
-            MACB_PROG(4);
-            double y0, y1, y2, y3;
-            int stop_seen;
-            unsigned int spins = 0;
-            while (true) {
-                bool ok = true;
-                y0 = y1 = y2 = y3 = 0.0;
-                stop_seen = 0;
-                for (unsigned int b = lane; b < ncta; b += 32) {
-                    double r0, r1, r2, r3;
-                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                 : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)b * 4) : "memory");
-                    ok = ok && (r0 == r0) && (r1 == r1) && (r2 == r2) && (r3 == r3);
-                    if (b == 0) stop_seen = (__double_as_longlong(r2) < 0) ? 1 : 0;
-                    y0 += r0; y1 += r1; y2 += fabs(r2); y3 += r3;
-                }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > (1u << 18)) {
-#ifdef MACB_DEBUG_VEC
-                    if (lane == 0 && atomicAdd(&g_dbg_count, 1) < 12) printf("[vec] t=%lld cta %d phase %d: inbox incomplete\n", (long long)clock64(), (int)blockIdx.x, phase);
-#endif
-                    give_up = 1;
-                    break;
-                }
-            }
-#ifdef MACB_PTIMING
-            tb2 = clock64();
-#endif
-            const double t = warp_sum4(y0, y1, y2, y3, lane);
-            if ((lane & 7) == 0) tot[lane >> 3] = t;
-            if (lane == 0) stop_sm = stop_seen;
-            for (unsigned int b = lane; b < ncta; b += 32) st_sector(const_cast<double*>(mine) + (size_t)b * 4, nanv, nanv, nanv, nanv);
-#ifdef MACB_PTIMING
-            tb3 = clock64();
-#endif
-        }
-        __syncthreads();
-        MACB_PROG(5);
-        // ---- coefficients (every thread, identical arithmetic) and pass B: the CTA's rows of u_{phase+1}
-        const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
-        const int stop_all = stop_sm;
-        const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
-#ifdef MACB_PTIMING
-        t_coef = clock64();
-#endif
-        if (has_row) {
-            const double un = fma(cf.k1, zr, fma(cf.k2, su, cf.k3 * sq)) + cf.k4;
-#ifdef MACB_DEBUG_VEC
-            if (un != un && atomicAdd(&g_dbg_count, 1) < 12)
-                printf("[vec] cta %d row %d phase %d: u_next is NaN: zr %g su %g sq %g k %g %g %g %g P %g %g %g %g\n", (int)blockIdx.x, row, phase, zr, su, sq,
-                       cf.k1, cf.k2, cf.k3, cf.k4, P1, P2, P3, P4);
-#endif
-            __stcg(Un + row, un);
-            __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
-            __stcg(const_cast<double*>(U) + row, nanv);   // poison: this buffer is the target of phase + 1's pass B
-            sq = su;
-            su = un;
-        }
-        if (blockIdx.x == 0 && tid == 0) {
-            a.alpha[phase] = cf.alpha;
-            a.beta[phase] = cf.beta;
-            if (a.ab_host)
-                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(cf.alpha), "d"(cf.beta) : "memory");
-        }
-        beta_prev = cf.binv;
-        usum_prev = P4;
-        MACB_PROG(6);
-#ifdef MACB_PTIMING
-        if (tid == 0 && a.timing && it < 64) {
-            long long* e = a.timing + (size_t)64 * a.ncta * 5 + ((size_t)it * a.ncta + blockIdx.x) * 4;
-            e[0] = tb0; e[1] = tb1; e[2] = tb2; e[3] = tb3;
-            long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 4;
-            t[0] = t_start; t[1] = t_rows; t[2] = clock64(); t[3] = (long long)atomicExch(&dbg_retries, 0);
-            a.timing[(size_t)64 * a.ncta * 4 + (size_t)it * a.ncta + blockIdx.x] = t_p1;
-        }
-#endif
-        cur ^= 1;
-        ++phase;
-        if (stop_all) break;
-    }
-#undef MACB_DST
-    if (blockIdx.x == 0 && tid == 0) {
-        a.st->phase = phase;
-        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
-        a.st->cur = cur;
-        a.st->beta_prev = beta_prev;
-        a.st->usum_prev = usum_prev;
-    }
-}
-
-// ---- K3, pipelined form of k_lanczos_vec: the reduction leaves the critical path -------------------------------------------
-// k_lanczos_vec spends a quarter of every step in the grid-wide exchange of the four partial sums (three dependent L2 round
+// ---- K3, pipelined jagged-diagonal form (default): the reduction leaves the critical path ---------------------------------------
+// Its predecessor (round 1's k_lanczos_vec: same layout, plain Lanczos) spent a quarter of every step in the grid-wide exchange of the four partial sums (three dependent L2 round
 // trips) plus the wait for the slowest CTA, because the coefficients alpha_j, beta_j of step j depend on z_j = L u_j, the
 // result of that very step's SpMV.  Here the recurrence is rearranged (Ghysels/Vanroose-style pipelining) so that the SpMV
 // and the reduction of a step are independent of each other:
@@ -1628,7 +949,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_vec(LzPersistArgs a, LzJ
 // these accesses bypass L1) never shows a reader an older value than one it has already seen.  The owner keeps the TAGGED
 // value in its own registers, so every CTA multiplies with the same z_j; the perturbation is one ulp of the gathered operand,
 // the size of the rounding error of the product it enters.  The records carry the same tag in the first of their four doubles
-// (a 32-byte sector is written and read as one transaction).  k_lanczos_vec needed a release fence per step (2 000 cycles
+// (a 32-byte sector is written and read as one transaction).  The predecessor needed a release fence per step (2 000 cycles
 // with a thousand stores in flight, measured) plus 8 + 32 bytes of poison per node and inbox slot to get the same guarantee.
 __device__ __forceinline__ double lz_tagged(double v, int tag) {
     return __longlong_as_double((__double_as_longlong(v) & ~1ll) | (long long)tag);
@@ -1719,10 +1040,8 @@ struct RrArgs {
     double* b2;
     double* binv;
     double* s;
-    double* dp;            // twisted factorisation: forward / backward pivots and multipliers, [cap + 2] each
-    double* dm;
-    double* lp;
-    double* um;
+    double* dp;            // eigenvector recurrences from the top / from the bottom, [cap + 2] each (global fall-back of the
+    double* dm;            // shared-memory copies)
     double* coef;          // out [cap + 1]: s_t / beta_t
     RrOut* out;
     int* dev_stop;
@@ -1826,49 +1145,6 @@ __device__ __forceinline__ double rr_block_sum(double v, double* red /*[32]*/) {
 // sequence with ~250 cycles of latency on this chip, and the Sturm recurrence below is one long chain of them: the check of a
 // T_190 took 180 us and the solver overshot its stopping point by 60 % (measured); the recurrence is backward stable with
 // respect to such last-bit errors (they are relative perturbations of the matrix entries of the same size).
-template <int NEWTON = 2>
-__device__ __forceinline__ double rr_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < NEWTON; ++it) {
-        const double e = fma(-x, r, 1.0);
-        r = fma(r, e, r);
-    }
-    return r;
-}
-
-// The two pivot chains of the twisted factorisation of T_k - theta I (one thread each) and the two product sweeps.  Separate
-// functions with __restrict__ arrays: written inline on aliasing pointers, every load waits for the previous row's stores.
-// NEWTON = 1 (reciprocals to ~1e-12) for the checks, which need the estimate to 10 %; 2 for the accepted pair.
-template <int NEWTON>
-__device__ __forceinline__ void rr_pivots_down(const double* __restrict__ a, const double* __restrict__ b, int k, double theta, double tiny,
-                                               double* __restrict__ dp, double* __restrict__ lp) {
-    double d = a[0] - theta;
-    for (int i = 0; i + 1 < k; ++i) {
-        if (fabs(d) < tiny) d = (d < 0.0 ? -tiny : tiny);
-        dp[i] = d;
-        const double bn = b[i + 1];
-        const double l = bn * rr_rcp<NEWTON>(d);
-        lp[i] = l;
-        d = fma(-l, bn, a[i + 1] - theta);
-    }
-    dp[k - 1] = d;
-}
-template <int NEWTON>
-__device__ __forceinline__ void rr_pivots_up(const double* __restrict__ a, const double* __restrict__ b, int k, double theta, double tiny,
-                                             double* __restrict__ dm, double* __restrict__ um) {
-    double d = a[k - 1] - theta;
-    for (int i = k - 2; i >= 0; --i) {
-        if (fabs(d) < tiny) d = (d < 0.0 ? -tiny : tiny);
-        dm[i + 1] = d;
-        const double bn = b[i + 1];
-        const double u = bn * rr_rcp<NEWTON>(d);
-        um[i] = u;
-        d = fma(-u, bn, a[i] - theta);
-    }
-    dm[0] = d;
-}
 // Eigenvector of T_k for theta without a single division: the three-term recurrence run from the top (f) and from the bottom
 // (g), one thread each, joined at the index r of the largest |f| -- the vector of the twisted factorisation at that r, obtained
 // through the minors instead of the pivots: ~25 cycles per row instead of ~100 (a pivot costs a reciprocal).  The recurrence from
@@ -1904,22 +1180,86 @@ __device__ __forceinline__ void rr_three_term_up(const double* __restrict__ a, c
     }
 }
 
-__device__ __forceinline__ bool rr_sweep_up(const double* __restrict__ lp, int r, double* __restrict__ sv) {
-    double v = 1.0;
-    sv[r] = 1.0;
-    for (int i = r - 1; i >= 0; --i) {
-        v = -lp[i] * v;
-        sv[i] = v;
-    }
-    return fabs(v) < 1e140 || r == 0;   // (the entries decay away from r; a runaway product shows in the last one)
+// The same two recurrences with every array in SHARED memory (32-bit shared addresses), four rows per trip, the entries of the
+// next trip requested before the current one is worked on: the chain is then the two dependent floating-point operations per
+// row.  (Through generic pointers the compiler keeps the loads inside the chain: 240 cycles per row, measured.)
+__device__ __forceinline__ double rr_lds(unsigned int addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ bool rr_sweep_down(const double* __restrict__ um, int r, int k, double* __restrict__ sv) {
-    double v = 1.0;
-    for (int i = r; i + 1 < k; ++i) {
-        v = -um[i] * v;
-        sv[i + 1] = v;
+__device__ __forceinline__ void rr_sts(unsigned int addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+__device__ __forceinline__ void rr_three_term_down_smem(unsigned int a_sh, unsigned int b_sh, unsigned int binv_sh, unsigned int f_sh, int k,
+                                                        double theta) {
+    double f0 = 1.0;
+    rr_sts(f_sh, 1.0);
+    if (k < 2) return;
+    double f1 = -(rr_lds(a_sh) - theta) * rr_lds(binv_sh + 8u);
+    rr_sts(f_sh + 8u, f1);
+    double an[4], bn[4], vn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // rows 1..4 (the arrays reach at least k + 8: reads past the end are harmless)
+        an[j] = rr_lds(a_sh + 8u * (1 + j));
+        bn[j] = rr_lds(b_sh + 8u * (1 + j));
+        vn[j] = rr_lds(binv_sh + 8u * (2 + j));
     }
-    return fabs(v) < 1e140;
+    for (int i = 1; i + 1 < k; i += 4) {
+        double ac[4], bc[4], vc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ac[j] = an[j]; bc[j] = bn[j]; vc[j] = vn[j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            an[j] = rr_lds(a_sh + 8u * (unsigned int)(i + 4 + j));
+            bn[j] = rr_lds(b_sh + 8u * (unsigned int)(i + 4 + j));
+            vn[j] = rr_lds(binv_sh + 8u * (unsigned int)(i + 5 + j));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j + 1 < k) {
+                const double fn = -fma(ac[j] - theta, f1, bc[j] * f0) * vc[j];
+                rr_sts(f_sh + 8u * (unsigned int)(i + j + 1), fn);
+                f0 = f1;
+                f1 = fn;
+            }
+        }
+    }
+}
+// returns false if the recurrence overflowed (the caller then uses the rescaling global-memory version)
+__device__ __forceinline__ bool rr_three_term_up_smem(unsigned int a_sh, unsigned int b_sh, unsigned int binv_sh, unsigned int g_sh, int k,
+                                                      double theta) {
+    double g0 = 1.0;   // g_{k-1}
+    rr_sts(g_sh + 8u * (unsigned int)(k - 1), 1.0);
+    if (k < 2) return true;
+    double g1 = -(rr_lds(a_sh + 8u * (unsigned int)(k - 1)) - theta) * rr_lds(binv_sh + 8u * (unsigned int)(k - 1));   // g_{k-2}
+    rr_sts(g_sh + 8u * (unsigned int)(k - 2), g1);
+    double an[4], bn[4], vn[4];
+    auto fetch = [&](int i) {   // rows i, i-1, i-2, i-3 (indices clamped at 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned int r = (unsigned int)max(i - j, 0);
+            an[j] = rr_lds(a_sh + 8u * r);
+            bn[j] = rr_lds(b_sh + 8u * (r + 1u));
+            vn[j] = rr_lds(binv_sh + 8u * r);
+        }
+    };
+    fetch(k - 2);
+    for (int i = k - 2; i >= 1; i -= 4) {
+        double ac[4], bc[4], vc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ac[j] = an[j]; bc[j] = bn[j]; vc[j] = vn[j]; }
+        fetch(i - 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i - j >= 1) {
+                const double gn = -fma(ac[j] - theta, g1, bc[j] * g0) * vc[j];   // g_{i-j-1}
+                rr_sts(g_sh + 8u * (unsigned int)(i - j - 1), gn);
+                g0 = g1;
+                g1 = gn;
+            }
+        }
+    }
+    return fabs(g1) < 1e250 && fabs(g0) < 1e250;
 }
 
 // True iff T_k has an eigenvalue below x: a sign change in the sequence of leading principal minors p_i(x) of T - x I,
@@ -2022,7 +1362,7 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
     double* const b_s = smem + 2 * cap_s;
     double* const binv_s = smem + 3 * cap_s;
     double* const w_s = smem + 4 * cap_s;   // f (top-down), g (bottom-up), s
-    __shared__ int s_fail, s_kbreak, s_vec_ok, s_vec_ok2, s_kr;
+    __shared__ int s_fail, s_kbreak, s_kr;
     __shared__ double a_pad_save[8], b2_pad_save[8];
     __shared__ double red4[128];
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
@@ -2232,8 +1572,15 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
         // index r of the largest entry of the one from the top.  (A recurrence from the top alone cannot resolve the tail of a
         // converged pair, and est = |beta_k s_{k-1}| needs exactly that tail -- measured: the estimate stalled at 1e-3 of a pair
         // whose true residual had long passed 1e-9.)
-        if (tid == 0) rr_three_term_down(pa, pb, pbinv, k, theta, pdp);
-        else if (tid == 32) rr_three_term_up(pa, pb, pbinv, k, theta, pdm);
+        if (in_s) {
+            const unsigned int b_sh = (unsigned int)__cvta_generic_to_shared(b_s), binv_sh = (unsigned int)__cvta_generic_to_shared(binv_s);
+            if (tid == 0) rr_three_term_down_smem(a_sh, b_sh, binv_sh, (unsigned int)__cvta_generic_to_shared(pdp), k, theta);
+            else if (tid == 32 && !rr_three_term_up_smem(a_sh, b_sh, binv_sh, (unsigned int)__cvta_generic_to_shared(pdm), k, theta))
+                rr_three_term_up(pa, pb, pbinv, k, theta, pdm);
+        } else {
+            if (tid == 0) rr_three_term_down(pa, pb, pbinv, k, theta, pdp);
+            else if (tid == 32) rr_three_term_up(pa, pb, pbinv, k, theta, pdm);
+        }
         __syncthreads();
         {   // r = argmax |f_i| (ties -> smallest index)
             double best = -1.0;
@@ -2270,9 +1617,13 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
         exhausted = invariant || need >= R.k_limit;
         s_inv = inv;
         s_vok = vec_ok;
-        if (!(est < target || exhausted) || !vec_ok || polish == 1 || k == 1) break;
-        // accepted on an approximate theta: polish it with the Rayleigh quotient of s (error ~ (d theta)^2 / gap) and redo the
-        // twisted factorisation, so that the Ritz coefficients handed to k_ritz are those of an accurate eigenpair of T_k
+        if (!vec_ok || polish == 1 || k == 1) break;
+        // theta is known to ~1e-7 only (multisection stops there, a frozen theta is the previous check's).  The vector just
+        // computed is one step of inverse iteration with that shift, so its Rayleigh quotient is accurate to
+        // d(theta) (d(theta) / gap)^2 -- Rayleigh-quotient iteration converges cubically -- and the SECOND pass, with the
+        // polished theta, gives the tail of the eigenvector that the estimate needs: an error d(theta) in the shift
+        // contaminates the vector with other Ritz vectors (last entries ~0.1) at the level d(theta) / gap, far above the
+        // 1e-10 the tail of a converged pair has (measured: with theta to 1e-7 and no polish the estimate stalls at 5e-4).
         {
             double num = 0.0;
             for (int i = tid; i < k; i += nt) {
@@ -2610,172 +1961,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
 constexpr int kSmallSlots = 12;   // slots per thread  => nnz <= 12 * 1024
 constexpr int kSmallRows = 3;     // rows per thread   => n   <=  3 * 1024
 
-__global__ void __launch_bounds__(kPBlock, 1) k_lanczos_small(LzPersistArgs a, const double* __restrict__ diag) {
-    extern __shared__ double smem_small[];
-    const int n = a.n;
-    const int nnz = a.rp[n];
-    double* __restrict__ sec = smem_small;                       // [3 n]
-    double* __restrict__ prod = sec + 3 * (size_t)n;             // [nnz]
-    double* __restrict__ wts = prod + nnz;                       // [nnz]
-    double* __restrict__ tvec = wts + nnz;                       // [n]  u_next - k4, materialised once per phase
-    __shared__ double ks[4];
-    __shared__ double sm[4 * kPWarps];
-    __shared__ double tot[4];
-    __shared__ int stop_small;
-    if (threadIdx.x == 0) stop_small = 0;
-    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
-
-    int pc[kSmallSlots];
-#pragma unroll
-    for (int j = 0; j < kSmallSlots; ++j) {
-        const int i = threadIdx.x + kPBlock * j;
-        pc[j] = (i < nnz) ? a.col[i] : 0;
-        if (i < nnz) wts[i] = a.val[i];
-    }
-    int rs0[kSmallRows], rs1[kSmallRows];
-    double rd[kSmallRows];
-#pragma unroll
-    for (int r = 0; r < kSmallRows; ++r) {
-        const int row = threadIdx.x + kPBlock * r;
-        rs0[r] = (row < n) ? a.rp[row] : 0;
-        rs1[r] = (row < n) ? a.rp[row + 1] : 0;
-        rd[r] = (row < n) ? diag[row] : 0.0;
-    }
-    int phase = a.st->phase;
-    double k1 = a.st->k1, k2 = a.st->k2, k3 = a.st->k3, k4 = a.st->k4;
-    double beta_prev = a.st->beta_prev, usum_prev = a.st->usum_prev;   // beta_prev: 1/beta of the last completed step
-    const double inv_n = 1.0 / (double)a.n;
-    double* __restrict__ G = a.sect[0];
-    for (int i = threadIdx.x; i < n; i += kPBlock) {
-        double z, u, q, d;
-        ld_sector(G + 4 * (size_t)i, z, u, q, d);
-        sec[3 * i] = z;
-        sec[3 * i + 1] = u;
-        sec[3 * i + 2] = q;
-    }
-    __syncthreads();
-    int stop_probe = 0;
-    bool stop_all = false;
-    double pend_alpha = 0.0, pend_beta = 0.0;
-#ifdef MACB_PTIMING
-    const long long t_begin = clock64();
-    const int phase_begin = phase;
-    long long t_p1 = 0, t_p2 = 0, t_red = 0;
-#endif
-
-    for (int it = 0; it < a.nphases && !stop_all; ++it, ++phase) {
-#ifdef MACB_PTIMING
-        const long long tt0 = clock64();
-#endif
-        double* __restrict__ bj = a.basis + (size_t)phase * a.ld;
-        // host stop flag: requested every 8th phase, looked at 7 phases later (a host-memory load takes microseconds)
-        if (threadIdx.x == 0 && a.stop && (it & 7) == 0)
-            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(stop_probe) : "l"(a.stop));
-        // one shared-memory gather per slot instead of three: shared-memory bandwidth (128 B/clk) is what bounds
-        // a single-SM step
-#pragma unroll
-        for (int r = 0; r < kSmallRows; ++r) {
-            const int row = threadIdx.x + kPBlock * r;
-            if (row < n) tvec[row] = fma(k1, sec[3 * row], fma(k2, sec[3 * row + 1], k3 * sec[3 * row + 2]));
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kSmallSlots; ++j) {
-            const int i = threadIdx.x + kPBlock * j;
-            if (i < nnz) {
-                const double w = wts[i];
-                prod[i] = (w != 0.0) ? w * tvec[pc[j]] : 0.0;
-            }
-        }
-        __syncthreads();
-#ifdef MACB_PTIMING
-        const long long tt1 = clock64();
-#endif
-        double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
-#pragma unroll
-        for (int r = 0; r < kSmallRows; ++r) {
-            const int row = threadIdx.x + kPBlock * r;
-            if (row < n) {
-                double acc = 0.0;
-                for (int i = rs0[r]; i < rs1[r]; ++i) acc += prod[i];
-                const double u = sec[3 * row + 1];
-                const double t = tvec[row];
-                const double un = t + k4;
-                const double zn = fma(rd[r], t, -acc);
-                sec[3 * row] = zn;
-                sec[3 * row + 1] = un;
-                sec[3 * row + 2] = u;
-                __stcs(bj + row, un);   // streaming: the basis must not push the matrix out of L2
-                p1 = fma(un, zn, p1);
-                p2 += zn;
-                p3 = fma(un, un, p3);
-                p4 += un;
-            }
-        }
-#ifdef MACB_PTIMING
-        const long long tt2 = clock64();
-#endif
-        double v[4] = {p1, p2, p3, p4};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-        if (wl == 0)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sm[i * kPWarps + warp] = v[i];
-        __syncthreads();
-        if (warp < 4) {
-            double x = sm[warp * kPWarps + wl];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (wl == 0) tot[warp] = x;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {   // one thread does the scalar algebra (double sqrt / divide are ~100-instruction sequences)
-            const double P1 = tot[0], P2 = tot[1], P3 = tot[2], P4 = tot[3];
-            const LzCoef cf = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? beta_prev : 0.0, usum_prev, inv_n);
-            ks[0] = cf.k1; ks[1] = cf.k2; ks[2] = cf.k3; ks[3] = cf.k4;
-            beta_prev = cf.binv;
-            usum_prev = P4;
-            pend_alpha = cf.alpha;
-            pend_beta = cf.beta;
-            if (a.stop && (it & 7) == 7) stop_small = stop_probe;
-        }
-        __syncthreads();
-        k1 = ks[0]; k2 = ks[1]; k3 = ks[2]; k4 = ks[3];
-        if (threadIdx.x == 0) {   // after the barrier: the other warps are already in the next step
-            a.alpha[phase] = pend_alpha;
-            a.beta[phase] = pend_beta;
-            if (a.ab_host)
-                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a.ab_host + 2 * (size_t)phase), "d"(pend_alpha), "d"(pend_beta) : "memory");
-        }
-        stop_all = (stop_small != 0);
-#ifdef MACB_PTIMING
-        { const long long tt3 = clock64(); t_p1 += tt1 - tt0; t_p2 += tt2 - tt1; t_red += tt3 - tt2; }
-#endif
-        // no barrier needed here: the next pass 1 only reads `sec`, which every thread finished writing before the
-        // two barriers above; `tot` / `sm` are rewritten only after the next pass-1 barrier
-    }
-#ifdef MACB_PTIMING
-    if (threadIdx.x == 0 && a.timing) {
-        a.timing[0] = clock64() - t_begin; a.timing[1] = phase - phase_begin; a.timing[2] = t_p1; a.timing[3] = t_p2; a.timing[4] = t_red;
-    }
-#endif
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kPBlock)
-        st_sector(G + 4 * (size_t)i, sec[3 * i], sec[3 * i + 1], sec[3 * i + 2], diag[i]);
-    if (threadIdx.x == 0) {
-        a.st->phase = phase;
-        if (a.stop) const_cast<int*>(a.stop)[1] = phase;   // host-mapped: read after the stream synchronise, no extra copy
-        a.st->cur = 0;
-        a.st->k1 = k1; a.st->k2 = k2; a.st->k3 = k3; a.st->k4 = k4;
-        a.st->beta_prev = beta_prev;
-        a.st->usum_prev = usum_prev;
-    }
-}
-
 // ---- K3, single-CTA form, second generation (default for small graphs) ------------------------------------------
-// Same problem class as k_lanczos_small, organised like k_lanczos_vec: the current Lanczos vector is materialised in
+// Organised like the grid kernel: the current Lanczos vector is materialised in
 // shared memory, every thread keeps (u_j, u_{j-1}) of its rows in registers, the block-wide sums are finished by EVERY
 // warp redundantly (one shared-memory round instead of a second stage + barrier), the coefficient chain runs on all
 // threads.  Three CTA barriers per step instead of six.  State hand-over through the sector buffer is compatible with
@@ -3051,58 +2238,6 @@ __global__ void __launch_bounds__(kBlock) k_sel_init(SelState* st, long long k) 
         st->eq_total = 0;
     }
     st->hist[threadIdx.x] = 0u;
-}
-
-__global__ void __launch_bounds__(kBlock) k_sel_hist(int64_t m, const double* __restrict__ g, SelState* st, int shift) {
-    __shared__ unsigned int sh[256];
-    sh[threadIdx.x] = 0u;
-    __syncthreads();
-    const unsigned long long prefix = st->prefix, mask = st->mask;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t mceil = ((m + 31) / 32) * 32;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mceil; e += stride) {
-        bool ok = false;
-        unsigned int d = 0xffffffffu;
-        if (e < m) {
-            unsigned long long key = order_key(g[e]);
-            ok = ((key & mask) == prefix);
-            d = ok ? (unsigned int)((key >> shift) & 0xffull) : 0xffffffffu;
-        }
-        // warp-aggregated histogram update (early digits are nearly constant across the array)
-        unsigned int peers = __match_any_sync(0xffffffffu, d);
-        if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[d], (unsigned int)__popc(peers));
-    }
-    __syncthreads();
-    unsigned int c = sh[threadIdx.x];
-    if (c) atomicAdd(&st->hist[threadIdx.x], c);
-}
-
-// One block of 256 threads: walk the histogram from the top digit down to the bucket holding the
-// `remaining`-th largest element; fix that digit.
-__global__ void __launch_bounds__(kBlock) k_sel_pick(SelState* st, int shift) {
-    __shared__ unsigned long long suf[256];
-    const int t = threadIdx.x;
-    const unsigned int h = st->hist[t];
-    suf[t] = h;
-    __syncthreads();
-    // inclusive suffix sum: suf[t] = sum_{d >= t} hist[d]
-    for (int o = 1; o < 256; o <<= 1) {
-        unsigned long long add = (t + o < 256) ? suf[t + o] : 0ull;
-        __syncthreads();
-        suf[t] += add;
-        __syncthreads();
-    }
-    const long long rem = st->remaining;
-    const unsigned long long above = suf[t] - h;   // elements in digits > t
-    __syncthreads();
-    if ((long long)above < rem && (long long)suf[t] >= rem) {
-        st->prefix |= ((unsigned long long)t) << shift;
-        st->mask |= 0xffull << shift;
-        st->remaining = rem - (long long)above;
-        st->count_gt += (long long)above;
-        st->eq_total = (long long)h;
-    }
-    st->hist[t] = 0u;
 }
 
 // ---- K5, two-pass form: one 15-bit histogram of the whole array + an exact select inside the chosen bin ------------------------
@@ -3482,12 +2617,6 @@ __global__ void __launch_bounds__(kBlock) k_rr_reset(double* __restrict__ alpha,
 __global__ void k_clear_lp_scalars(LzScalars* sc) {
     sc->gs_minus_x = 0.0;
     sc->nsel = 0;
-}
-
-__global__ void k_set_lanczos_start(LzScalars* sc, double* beta, double* usum, double beta0) {
-    sc->step = 0;
-    beta[0] = beta0;
-    usum[0] = 0.0;
 }
 
 }  // namespace macb

@@ -172,16 +172,14 @@ def test_warm_start_reaches_the_same_pair():
     mac.close()
 
 
-@pytest.mark.parametrize("env", [{"MACB_LANCZOS": "graph"}, {"MACB_PERSIST_V": "1"}, {"MACB_ASYNC": "0"}, {"MACB_NO_JDS": "1"}, {"MACB_JDS_SORT": "0"}, {"MACB_NO_VEC": "1"},
-                                 {"MACB_NO_PIPE": "1"},
-                                 {"MACB_NO_VEC": "1", "MACB_JDS_SORT": "0"},
-                                 {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
-                                 {"MACB_PERSIST_V": "1", "MACB_ASYNC": "0", "MACB_PERSIST_STREAM": "1"}])
+@pytest.mark.parametrize("env", [{"MACB_HOST_RR": "1"}, {"MACB_NO_PIPE": "1"}, {"MACB_PERSIST_V": "1"}, {"MACB_NO_JDS": "1"},
+                                 {"MACB_JDS_SORT": "0"}, {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
+                                 {"MACB_PERSIST_V": "1", "MACB_HOST_RR": "1"}])
 def test_lanczos_engines_agree(monkeypatch, env):
-    """The default engine (k_lanczos_vec: materialised Lanczos vector, column-sorted slots, jagged-diagonal staging,
-    asynchronous host Rayleigh-Ritz) against the alternatives kept for A/B: two-kernel CUDA-graph engine, row-parallel
-    persistent kernel, synchronous batches, CSR-ordered slot kernel with and without the shared-memory column cache,
-    jagged-diagonal kernels without column sorting, 32-byte-sector kernel k_lanczos_jds."""
+    """The default engine (k_lanczos_pipe: pipelined shifted Lanczos on the jagged-diagonal layout, stop decision by the
+    on-device Rayleigh-Ritz CTA) against the alternatives: the same kernel driven by the host Rayleigh-Ritz, the chunked
+    slot-parallel fall-back (k_lanczos_slots, with and without its column cache), the row-parallel general fall-back
+    (k_lanczos_persist), and the layout without column sorting."""
     fixed, cand, n = synth.chain_plus_random(4000, 40000, seed=3, weighted=True)
     x = synth.first_k_init(40000, 8000)
     ref = MAC(fixed, cand, n)

@@ -192,7 +192,7 @@ def test_synthetic_generators_are_deterministic():
 
 @pytest.mark.parametrize("sorted_slots,bankfit", [(False, False), (True, False), (True, True)])
 def test_jagged_diagonal_layout_invariants(sorted_slots, bankfit):
-    """The layout k_lanczos_vec / k_lanczos_jds read (csrc/api.cu build_jds_layout), checked on the host: engine
+    """The layout k_lanczos_pipe reads (csrc/api.cu build_jds_layout), checked on the host: engine
     numbering is a within-CTA permutation by decreasing length, every row owns exactly one position per diagonal
     jd[d] + t, positions tile the CTA's slot range, and every slot still carries its (row, column, edge) triple."""
     from mac_b200 import _lib

@@ -19,7 +19,7 @@ def run(tag, n, m, k):
     mac.close()
 
 run("small", 600, 3000, 600)            # k_lanczos_small
-run("multi-CTA", 6000, 40000, 8000)     # k_lanczos_vec, several CTAs
+run("multi-CTA", 6000, 40000, 8000)     # k_lanczos_pipe, several CTAs
 for env in ({"MACB_NO_VEC": "1"}, {"MACB_NO_JDS": "1"}, {"MACB_PERSIST_V": "1"}):
     os.environ.update(env)
     run(str(env), 6000, 40000, 8000)
