@@ -2554,14 +2554,15 @@ __global__ void __launch_bounds__(kBlock) k_sel_apply(int64_t m, int64_t chunk, 
 
 // ---- FW update: x <- x + gamma (s - x)  (frankwolfe.py:76), candidate edge weights refreshed -------
 // The three roundings (s - x, gamma * (.), x + (.)) are kept separate, as numpy evaluates them.
+// (x_out may be x itself, or a second buffer: the pipelined Frank-Wolfe loop keeps the iterate it has not yet accepted)
 __global__ void __launch_bounds__(kBlock) k_fw_update(int64_t m, double gamma, const uint8_t* __restrict__ sel,
                                                       const double* __restrict__ kappa, double tol,
-                                                      double* __restrict__ x, double* __restrict__ ew_cand) {
+                                                      const double* x, double* x_out, double* __restrict__ ew_cand) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
         double xe = x[e];
         double s = sel[e] ? 1.0 : 0.0;
         double xn = __dadd_rn(xe, __dmul_rn(gamma, __dsub_rn(s, xe)));
-        x[e] = xn;
+        x_out[e] = xn;
         ew_cand[e] = (xn > tol) ? xn * kappa[e] : 0.0;
     }
 }
