@@ -102,6 +102,13 @@ int macb_round_nearest(macb_handle h, const double* w, int64_t k, int decimals, 
 int macb_round_nearest_dense(int device, const double* w, const double* weights, int64_t m, int64_t k, int decimals,
                              double* rounded);
 
+/* lambda2(L(x_b)) for nb iterates xs[nb][m], cold solves at `tol`, ONE host synchronisation for the whole batch (every solve
+ * is enqueued behind the previous one; the stop decisions are taken on the device).  Replaces the loop of
+ * `value_fn(x)` = MAC.evaluate_objective calls in round_madow (rounding.py:63-75, mac.py:203-204) and the 3-5
+ * evaluate_objective calls per budget of examples/g2o_experiment.py:347-376.  resid (may be NULL) receives the residuals. */
+int macb_evaluate_batch(macb_handle h, const double* xs, int nb, double tol, double min_sel_tol, int max_steps,
+                        double* lambda2, double* resid);
+
 /* ---- whole Frank-Wolfe loop ------------------------------------------------------------------- */
 
 /* Replaces frank_wolfe (frankwolfe.py:10-79) specialised as MAC.solve calls it (mac.py:186-200):

@@ -59,6 +59,7 @@ def lib():
     _sig(L.macb_set_start, [H, _dp])
     _sig(L.macb_fiedler, [H, C.c_double, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int), _dp])
     _sig(L.macb_gradient, [H, _dp])
+    _sig(L.macb_evaluate_batch, [H, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp])
     _sig(L.macb_topk, [H, C.c_int64, _dp])
     _sig(L.macb_topk_dense, [C.c_int, _dp, C.c_int64, C.c_int64, _dp])
     _sig(L.macb_round_nearest, [H, _dp, C.c_int64, C.c_int, _dp])
@@ -270,6 +271,16 @@ class Handle:
         self._check(rc, "macb_fw_run")
         it = iters.value
         return w, u.value, {"iters": it, "f_hist": fh[:it].copy(), "u_hist": uh[:it].copy()}
+
+    def evaluate_batch(self, xs, tol=1e-8, min_sel_tol=1e-10, max_steps=0):
+        """lambda2(L(x_b)) for every row of xs, one host synchronisation (macb_evaluate_batch)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, self.m)
+        lam = np.zeros(len(xs))
+        res = np.zeros(len(xs))
+        rc = self._L.macb_evaluate_batch(self._h, _p(xs, _dp), len(xs), float(tol), float(min_sel_tol), int(max_steps), _p(lam, _dp),
+                                         _p(res, _dp))
+        self._check(rc, "macb_evaluate_batch")
+        return lam, res
 
     def sweep(self, comm, budgets, x_inits, max_iters=20, rel_gap_tol=1e-4, grad_norm_tol=1e-8, fiedler_tol=1e-8, min_sel_tol=1e-10,
               fiedler_max_steps=0, want_w=True):

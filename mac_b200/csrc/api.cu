@@ -1580,6 +1580,87 @@ int macb_fiedler(macb_handle h, double tol, int max_steps, int warm, double* lam
     });
 }
 
+// lambda2 of L(x_b) for a batch of iterates, with ONE host synchronisation: every solve (assemble, eigen-solve with the
+// stop decision on the device, residual) is enqueued behind the previous one and leaves its scalars in its own pinned slot.
+int macb_evaluate_batch(macb_handle h, const double* xs, int nb, double tol, double min_sel_tol, int max_steps, double* lambda2,
+                        double* resid) {
+    return guarded(h, [&]() {
+        if (nb < 0 || (nb > 0 && ((!xs && h->m > 0) || !lambda2))) throw ArgFail{"macb_evaluate_batch: bad arguments", MACB_ERR_ARG};
+        if (h->n < 2) throw ArgFail{"macb_evaluate_batch: need at least 2 nodes", MACB_ERR_ARG};
+        if (max_steps <= 0) max_steps = 20000;
+        int status = MACB_OK;
+        ensure_basis(h, max_steps);
+        const int64_t m = h->m;
+        auto one_by_one = [&](int b) {   // host-driven path (engines without the device-side decision, or a failed decision)
+            int rc = macb_set_x(h, xs + (size_t)b * m, min_sel_tol);
+            if (rc < 0) throw ArgFail{h->err, rc};
+            FiedlerResult fr;
+            rc = run_fiedler(h, tol, max_steps, 0, fr);
+            if (rc == MACB_NOT_CONVERGED) status = rc;
+            lambda2[b] = fr.lambda2;
+            if (resid) resid[b] = fr.resid;
+        };
+        if (!device_fiedler_available(h) || h->profile) {
+            for (int b = 0; b < nb; ++b) one_by_one(b);
+            return status;
+        }
+        LzScalars* hs = nullptr;
+        RrOut* hr = nullptr;
+        double* hx = nullptr;   // pinned staging of the iterates: a pageable source would serialise the copies with the host
+        CK(cudaMallocHost(&hs, sizeof(LzScalars) * std::max(nb, 1)));
+        CK(cudaMallocHost(&hr, sizeof(RrOut) * std::max(nb, 1)));
+        CK(cudaMallocHost(&hx, sizeof(double) * std::max<int64_t>(m, 1) * 2));
+        h->min_sel_tol = min_sel_tol;
+        cudaEvent_t copied[2] = {nullptr, nullptr};
+        CK(cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming));
+        for (int b = 0; b < nb; ++b) {
+            double* stage = hx + (size_t)(b & 1) * m;
+            if (b >= 2) CK(cudaEventSynchronize(copied[b & 1]));   // the staging half is free again
+            if (m) memcpy(stage, xs + (size_t)b * m, sizeof(double) * m);
+            if (m) CK(cudaMemcpyAsync(h->d_x, stage, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaEventRecord(copied[b & 1], h->stream));
+            if (m > 0) {
+                k_edge_weights<<<h->grid_for(m), kBlock, 0, h->stream>>>(m, h->d_x, h->d_kappa, min_sel_tol, h->d_ew + h->nf);
+                h->c_launches++;
+            }
+            launch_assemble(h, false);
+            h->have_x = true;
+            enqueue_fiedler_device(h, tol, max_steps, false);
+            CK(cudaMemcpyAsync(hs + b, h->d_sc, sizeof(LzScalars), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(hr + b, h->d_rr_out, sizeof(RrOut), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<int> redo;
+        for (int b = 0; b < nb; ++b) {
+            const LzScalars& sc = hs[b];
+            const RrOut& r = hr[b];
+            h->c_steps += r.phases;
+            h->c_spmv += r.phases;
+            const double res = (sc.lnorm > 0.0 && sc.vv > 0.0) ? sc.res1 / (std::sqrt(sc.vv) * sc.lnorm) : 1.0;
+            if (!(sc.lnorm > 0.0) || r.status <= 0 || r.k <= 0 || !(res < tol)) {
+                redo.push_back(b);
+                continue;
+            }
+            lambda2[b] = sc.vLv / sc.vv;
+            if (resid) resid[b] = res;
+        }
+        cudaEventDestroy(copied[0]);
+        cudaEventDestroy(copied[1]);
+        cudaFreeHost(hs);
+        cudaFreeHost(hr);
+        cudaFreeHost(hx);
+        for (int b : redo) {
+            h->c_dev_fallbacks++;
+            h->force_host_rr = true;
+            one_by_one(b);
+            h->force_host_rr = false;
+        }
+        h->have_g = false;
+        return status;
+    });
+}
+
 int macb_gradient(macb_handle h, double* g) {
     return guarded(h, [&]() {
         launch_gradient(h);

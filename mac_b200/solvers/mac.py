@@ -76,6 +76,14 @@ class MAC:
         self.last_info = info
         return lam
 
+    def evaluate_objectives(self, xs):
+        """lambda2(L(x)) for every row of `xs` -- `evaluate_objective` batched: all solves are enqueued back to back and the
+        host synchronises once (`macb_evaluate_batch`).  What Madow rounding with `max_iters > 1` (rounding.py:63-75) and the
+        3-5 evaluations per budget of g2o_experiment.py:347-376 call in a loop."""
+        lam, _ = self._h.evaluate_batch(xs, tol=self.fiedler_tol, min_sel_tol=self.min_selection_weight_tol,
+                                        max_steps=self.fiedler_max_steps)
+        return lam
+
     def fiedler_pair(self, x, tol=None, warm=False):
         """(lambda2, v2) of L(x) -- the device counterpart of fiedler.find_fiedler_pair(L(x))."""
         self._h.set_x(x, self.min_selection_weight_tol)

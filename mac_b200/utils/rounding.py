@@ -58,6 +58,13 @@ def round_madow(w, k, seed=None, value_fn=None, max_iters=1):
     """rounding.py:63-75."""
     if value_fn is None or max_iters == 1:
         return round_madow_base(w, k, seed)
+    batch = getattr(getattr(value_fn, "__self__", None), "evaluate_objectives", None)
+    if batch is not None and getattr(value_fn, "__name__", "") == "evaluate_objective":
+        # value_fn is MAC.evaluate_objective: draw all candidates first (same random stream: the evaluations draw nothing),
+        # evaluate them in one batched device call, keep the first best -- the same result as the loop below
+        xs = [round_madow_base(w, k, seed) for _ in range(max_iters)]
+        vals = batch(np.stack(xs))
+        return xs[int(np.argmax(vals))]   # argmax returns the FIRST maximum, as `val > best_val` does
     best_x, best_val = None, -np.inf
     for _ in range(max_iters):
         x = round_madow_base(w, k, seed)

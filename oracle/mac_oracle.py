@@ -271,6 +271,33 @@ class OracleMAC:
         return rounded, w, u
 
 
+def greedy_eig_subset(omac, k):
+    """mac/solvers/greedy_eig.py:86-155 restated with exact eigen-solves (`omac.problem`) in place of the CHOLMOD
+    factor up/down-dates (sksparse is not installable here, so the reference's own GreedyEig cannot run: this row's
+    parity is UNPINNED -- the restatement is checked for the greedy property only).  Returns (solution, evaluations)."""
+    m = len(omac.weights)
+    solution = np.zeros(m)
+    solution_l2, solution_grad = omac.problem(solution)
+    evaluations = 0
+    for _ in range(k):
+        best_idx, best_l2, best_grad = -1, 0.0, None
+        for j in range(m):
+            if solution[j] > 0:
+                continue
+            if solution_l2 + solution_grad[j] < best_l2:   # greedy_eig.py:118-120
+                continue
+            w = solution.copy()
+            w[j] = 1.0
+            l2, grad = omac.problem(w)
+            evaluations += 1
+            if l2 > best_l2 + 1e-8:                         # greedy_eig.py:137-141
+                best_idx, best_l2, best_grad = j, l2, grad
+        assert best_idx != -1
+        solution[best_idx] = 1.0
+        solution_l2, solution_grad = best_l2, best_grad
+    return solution, evaluations
+
+
 def naive_greedy_subset(weights, k):
     """solvers/baseline.py:9-16 (without the stray prints)."""
     weights = np.asarray(weights, dtype=float)

@@ -595,6 +595,59 @@ def test_zero_candidates_lp_and_fw_do_not_crash():
     h.close()
 
 
+# ------------------------------------------------------------------------------------------- batched evaluate_objective
+def test_batched_evaluate_objective_and_madow():
+    """macb_evaluate_batch == evaluate_objective one by one (bitwise: same kernels, same start vector), on a grid-engine graph
+    and on a single-SM graph; round_madow(value_fn=mac.evaluate_objective, max_iters > 1) goes through it and returns what
+    the reference loop (rounding.py:63-75) returns with the oracle's value_fn."""
+    from mac_b200.utils.rounding import round_madow
+    rng = np.random.default_rng(5)
+    for fixed, cand, n in (synth.chain_plus_random(3000, 30000, seed=5, weighted=True), synth.chain_plus_random(300, 900, seed=2, weighted=True)):
+        m = len(cand[0])
+        mac = MAC(fixed, cand, n)
+        xs = np.stack([(rng.random(m) < 0.3).astype(float) for _ in range(5)] + [rng.random(m)])
+        lam_b = mac.evaluate_objectives(xs)
+        lam_1 = np.array([mac.evaluate_objective(x) for x in xs])
+        assert np.array_equal(lam_b, lam_1)
+        o = orc.OracleMAC(fixed, cand, n)
+        assert np.allclose(lam_b, [o.evaluate_objective(x) for x in xs], rtol=1e-8)
+        mac.close()
+    fixed, cand, n = synth.chain_plus_random(200, 900, seed=2, weighted=True)
+    mac, o = MAC(fixed, cand, n), orc.OracleMAC(fixed, cand, n)
+    w = np.clip(rng.random(900) * 0.4, 0, 1)
+    w *= 180 / w.sum()
+    np.random.seed(11)
+    r_dev = round_madow(w, 180, value_fn=mac.evaluate_objective, max_iters=6)
+    np.random.seed(11)
+    r_ref = round_madow(w, 180, value_fn=o.evaluate_objective, max_iters=6)
+    assert np.array_equal(r_dev, r_ref) and r_dev.sum() == 180
+    mac.close()
+
+
+# ------------------------------------------------------------------------------------------- GreedyEig (SURVEY 8f rank 4)
+def test_greedy_eig_matches_oracle_restatement():
+    """mac/solvers/greedy_eig.py:86-155 on the device primitives vs the same loop on the oracle's eigen-solver."""
+    from mac_b200.solvers import GreedyEig
+    fixed, cand, n = synth.petersen_split()
+    ge = GreedyEig(fixed, cand, n)
+    sol, edges = ge.subset(3)
+    ref, _ = orc.greedy_eig_subset(orc.OracleMAC(fixed, cand, n), 3)
+    assert np.array_equal(sol, ref) and len(edges) == 3 and all(e.weight == 1.0 for e in edges)
+    ge.close()
+    fixed, cand, n = synth.chain_plus_random(60, 40, seed=6, weighted=True)
+    ge = GreedyEig(fixed, cand, n)
+    sol, edges = ge.subset(4)
+    o = orc.OracleMAC(fixed, cand, n)
+    ref, evals = orc.greedy_eig_subset(o, 4)
+    assert np.array_equal(sol, ref) and ge.evaluations == evals
+    assert abs(MAC(fixed, cand, n).evaluate_objective(sol) - o.evaluate_objective(ref)) <= 1e-8 * o.evaluate_objective(ref)
+    L = ge.combined_laplacian(sol)
+    assert abs(L - o.laplacian(ref)).max() == 0
+    lam, vec = ge.find_fiedler_pair(L)
+    assert abs(lam - o.evaluate_objective(ref)) <= 1e-8 * lam and np.allclose(ge.grad_from_fiedler(vec), o.gradient(vec))
+    ge.close()
+
+
 # ------------------------------------------------------------------------------------------- farm (multi-GPU)
 def _run_farm_ranks(world):
     """`world` processes, one per GPU, each running tools/farm_check.py (macb_sweep + ncclAllGather behind the C-ABI)."""

@@ -124,3 +124,16 @@ def test_g2o_reader_matches_fixture_when_reference_present(golden_dir):
     i, j, kappa, n = orc.read_g2o_edges(path)
     z = np.load(os.path.join(golden_dir, "g2o_intel.npz"))
     assert n == int(z["n"]) and (i == z["i"]).all() and (j == z["j"]).all() and np.array_equal(kappa, z["kappa"])
+
+
+def test_greedy_eig_restatement_is_greedy():
+    """greedy_eig.py:86-155 restated (oracle.greedy_eig_subset): every step picks an edge at least as good as any single-edge
+    alternative; lambda2 never decreases.  (The reference's own GreedyEig needs sksparse and cannot run here: unpinned.)"""
+    from mac_b200 import synth
+    fixed, cand, n = synth.petersen_split()
+    o = orc.OracleMAC(fixed, cand, n)
+    sol, evals = orc.greedy_eig_subset(o, 2)
+    assert sol.sum() == 2 and evals >= 2
+    first = max(range(6), key=lambda j: o.evaluate_objective(np.eye(6)[j]))
+    assert o.evaluate_objective(np.eye(6)[first]) <= max(o.evaluate_objective(np.eye(6)[j]) for j in np.flatnonzero(sol)) + 1e-8
+    assert o.evaluate_objective(sol) >= o.evaluate_objective(np.zeros(6)) - 1e-12
