@@ -434,7 +434,7 @@ void launch_spmv(macb_ctx* c, const double* x, double* y) {
     if (MODE == 0 && c->spmv_engine == 1 && c->d_sj_val) {
         SpmvJdsArgs j{c->sj_nchunks, c->d_sj_chunk_row, c->d_sj_chunk_slot, c->d_sj_chunk_jd, c->d_sj_col0, c->d_sj_jd, c->d_sj_perm,
                       c->d_sj_len, c->d_sj_word, c->d_sj_col, c->d_sj_val, c->d_diag, x, y};
-        const int grid = std::min(c->sj_nchunks, 4 * c->sm_count);
+        const int grid = std::min(c->sj_nchunks, kSjMinBlocks * c->sm_count);
         if (c->sj_col16) k_spmv_jds<true><<<grid, kSjBlock, 0, c->stream>>>(j);
         else k_spmv_jds<false><<<grid, kSjBlock, 0, c->stream>>>(j);
         CK(cudaGetLastError());
