@@ -217,13 +217,15 @@ int macb_sweep(macb_handle h, macb_comm_t comm, const int64_t* ks, int nk, const
 
 /* ---- host-only helpers (no GPU needed; exported for the CPU test-suite) ----------------------- */
 
-/* Host-side layout builder of the Lanczos kernels (jagged diagonals, column-sorted slots, bank-fitted product positions;
- * see build_jds_layout in csrc/api.cu for the format).  rp/col/eid: the union pattern of macb_host_build_pattern; CTA b owns
- * rows row_start[b] .. row_start[b+1]; stride > longest row.  Outputs: jrow[n], jlen[n], jcol[nnz], jeid[nnz], jd[ncta*stride].
+/* Host-side layout builder of the Lanczos kernel k_lanczos_pipe (32-row slices padded to their longest row with a lane stride of
+ * 33 doubles, column-sorted slots that carry the position of their product, bank-fitted positions; see build_slice_layout in
+ * csrc/api.cu for the format).  rp/col/eid: the union pattern of macb_host_build_pattern; CTA b owns rows row_start[b] ..
+ * row_start[b+1] (at most 1024 of them, fewer than 2^15 product positions; n < 2^17 - 1).  Outputs: jrow[n], jlen[n], jcol[nnz],
+ * jeid[nnz], jw[ncta*64] = (first position, entries per row) of every slice, positions[ncta] = product positions per CTA.
  * Replaces nothing in the reference (which rebuilds a CSR per iteration, graphs.py:58-98): exported so that the CPU test-suite
  * can check the layout's invariants without a GPU. */
-int macb_host_build_jds(int32_t n, const int32_t* rp, const int32_t* col, const int32_t* eid, int32_t ncta, const int32_t* row_start,
-                        int32_t stride, int sorted, int bankfit, int32_t* jrow, int32_t* jlen, int32_t* jcol, int32_t* jeid, int32_t* jd);
+int macb_host_build_slices(int32_t n, const int32_t* rp, const int32_t* col, const int32_t* eid, int32_t ncta, const int32_t* row_start,
+                           int bankfit, int32_t* jrow, int32_t* jlen, int32_t* jcol, int32_t* jeid, int32_t* jw, int32_t* positions);
 
 /* Smallest eigenpair of the symmetric tridiagonal T_k (diagonal a[0..k), off-diagonal b[1..k)):
  * bisection on the Sturm count + twisted factorisation.  This is the Rayleigh-Ritz step the

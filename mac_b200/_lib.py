@@ -80,7 +80,7 @@ def lib():
     _sig(L.macb_spmv_engine, [H, C.c_int])
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
-    _sig(L.macb_host_build_jds, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int32, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip])
+    _sig(L.macb_host_build_slices, [C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, C.c_int, _ip, _ip, _ip, _ip, _ip, _ip])
     _sig(L.macb_comm_unique_id, [C.c_char_p])
     _sig(L.macb_comm_init, [C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(H)])
     _sig(L.macb_comm_allgather, [H, C.c_void_p, C.c_void_p, C.c_int64])
@@ -416,9 +416,13 @@ def host_build_pattern(n, fi, fj, ci, cj):
     return rp, col[:nnz.value], eid[:nnz.value]
 
 
-def host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots=True, bankfit=True):
-    """Host helper (no GPU): the jagged-diagonal layout of k_lanczos_pipe for a given CTA partition
-    `row_start` (len ncta + 1).  Returns (jrow, jlen, jcol, jeid, jd[ncta, stride])."""
+SLICE_STRIDE = 33   # kLzSlice
+SLICE_TAB = 64      # kLzSliceTab
+
+
+def host_build_slices(n, rp, col, eid, row_start, bankfit=True):
+    """Host helper (no GPU): the sliced layout of k_lanczos_pipe for a given CTA partition `row_start` (len ncta + 1).
+    Returns (jrow, jlen, jcol, jeid, jw[ncta, 64], positions[ncta])."""
     L = lib()
     rp, col, eid, row_start = _i32(rp), _i32(col), _i32(eid), _i32(row_start)
     ncta = len(row_start) - 1
@@ -427,10 +431,10 @@ def host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots=True, bankfi
     jlen = np.empty(max(n, 1), dtype=np.int32)
     jcol = np.empty(max(nnz, 1), dtype=np.int32)
     jeid = np.empty(max(nnz, 1), dtype=np.int32)
-    jd = np.zeros(max(ncta * stride, 1), dtype=np.int32)
-    rc = L.macb_host_build_jds(n, _p(rp, _ip), _p(col, _ip), _p(eid, _ip), ncta, _p(row_start, _ip), int(stride),
-                               int(bool(sorted_slots)), int(bool(bankfit)), _p(jrow, _ip), _p(jlen, _ip), _p(jcol, _ip),
-                               _p(jeid, _ip), _p(jd, _ip))
+    jw = np.zeros(max(ncta * SLICE_TAB, 1), dtype=np.int32)
+    positions = np.zeros(max(ncta, 1), dtype=np.int32)
+    rc = L.macb_host_build_slices(n, _p(rp, _ip), _p(col, _ip), _p(eid, _ip), ncta, _p(row_start, _ip), int(bool(bankfit)),
+                                  _p(jrow, _ip), _p(jlen, _ip), _p(jcol, _ip), _p(jeid, _ip), _p(jw, _ip), _p(positions, _ip))
     if rc != MACB_OK:
-        raise MacbError(f"macb_host_build_jds failed ({rc})")
-    return jrow[:n], jlen[:n], jcol[:nnz], jeid[:nnz], jd.reshape(ncta, stride) if ncta * stride else jd
+        raise MacbError(f"macb_host_build_slices failed ({rc})")
+    return jrow[:n], jlen[:n], jcol[:nnz], jeid[:nnz], jw.reshape(ncta, SLICE_TAB), positions[:ncta]

@@ -109,7 +109,6 @@ struct macb_ctx {
     int *d_chunk_ptr = nullptr, *d_chunk_row = nullptr;
     size_t slots_smem = 0;
     int slots_cache_cols = 0, slots_prod_cap = 0;
-    bool jds_sorted = false;
     // chunked jagged-diagonal SpMV (k_spmv_jds): built on demand by macb_spmv_engine(h, 1)
     int spmv_engine = 0;           // 0: k_spmv (CSR, W lanes per row), 1: k_spmv_jds
     int sj_nchunks = 0;
@@ -160,7 +159,7 @@ struct macb_ctx {
     int *d_jrow = nullptr, *d_jlen = nullptr, *d_jcol = nullptr, *d_jeid = nullptr, *d_jd = nullptr;
     double* d_jval = nullptr;
     double* d_xrec = nullptr;      // all-to-all barrier inboxes of k_lanczos_jds
-    int jd_stride = 0;
+    int pipe_pos_cap = 0, pipe_slot_cap = 0;   // k_lanczos_pipe: product positions / slots per CTA (shared-memory sizes)
 
     // reductions / selection
     double* d_partials = nullptr;
@@ -485,8 +484,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         // cooperative: the solver CTA and the Rayleigh-Ritz CTA must be co-resident (the second stops the first)
         CK(cudaLaunchCooperativeKernel((void*)k_lanczos_small2, dim3(R.enabled ? 2 : 1), dim3(kPBlock), sparams, c->slots_smem, c->stream));
     } else if (c->persist_v == 5) {
-        LzJdsArgs J{c->d_row_start, c->d_jlen, c->d_jcol, c->d_jval, c->d_jd, c->jd_stride, c->slots_prod_cap, c->d_xrec,
-                    c->d_diag, c->d_jrow};
+        LzJdsArgs J{c->d_row_start, c->d_jcol, c->d_jval, c->d_jd, c->pipe_pos_cap, c->pipe_slot_cap, c->d_xrec, c->d_diag, c->d_jrow};
         LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
         RrArgs R = c->rr_launch;
         R.smem_doubles = (int)(c->pipe_smem / 8);
@@ -497,12 +495,12 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         void* pparams[] = {&a, &J, &P, &R};
         void* pf;
         switch (c->vec_batch) {
-            case 3: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 3> : (void*)k_lanczos_pipe<false, 3>; break;
-            case 4: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 4> : (void*)k_lanczos_pipe<false, 4>; break;
-            case 6: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 6> : (void*)k_lanczos_pipe<false, 6>; break;
-            case 7: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 7> : (void*)k_lanczos_pipe<false, 7>; break;
-            case 8: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 8> : (void*)k_lanczos_pipe<false, 8>; break;
-            default: pf = c->jds_sorted ? (void*)k_lanczos_pipe<true, 5> : (void*)k_lanczos_pipe<false, 5>; break;
+            case 3: pf = (void*)k_lanczos_pipe<3>; break;
+            case 4: pf = (void*)k_lanczos_pipe<4>; break;
+            case 6: pf = (void*)k_lanczos_pipe<6>; break;
+            case 7: pf = (void*)k_lanczos_pipe<7>; break;
+            case 8: pf = (void*)k_lanczos_pipe<8>; break;
+            default: pf = (void*)k_lanczos_pipe<5>; break;
         }
         CK(cudaLaunchCooperativeKernel(pf, dim3(a.ncta + (R.enabled ? 1 : 0)), dim3(kPBlock), pparams, c->pipe_smem, c->stream));
     } else if (c->persist_v == 3) {
@@ -520,18 +518,23 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
     }
 }
 
-// Jagged-diagonal layout of the Lanczos kernel k_lanczos_pipe (pure host code, also exported as
-// macb_host_build_jds for the CPU test-suite).  CTA b owns the rows row_start[b] .. row_start[b+1] and their slots
-// rp[row_start[b]] .. rp[row_start[b+1]].  Inside a CTA the rows are renumbered by decreasing length ("engine numbering",
-// jrow[engine row] = caller row, jlen = its length) so that diagonal d -- the d-th slot of every row that has one -- is the
-// contiguous range jd[b*stride + d] + t, t = engine row - row_start[b].  jcol holds ENGINE column ids.
-//   sorted = false: slot p of the CTA's range IS position p (jcol[p] = column of the product stored at p);
-//   sorted = true : the CTA's slots are stored in column order and carry their position: jcol = column | position << 17
-//                   (needs n <= 2^17 and <= 2^14 slots per CTA); which diagonal of its row a slot uses is free, and with
-//                   bankfit it is chosen so that the 16 positions of a half-warp fall into different 8-byte banks.
-void build_jds_layout(int n, const int32_t* rp, const int32_t* col, const int32_t* eid, int ncta, const int* row_start, int stride,
-                      bool sorted, bool bankfit, int* jrow, int* jlen, int* jcol, int* jeid, int* jd) {
-    std::vector<int> order, cnt, inv((size_t)n);   // inv[caller id] = engine id
+// Sliced layout of the Lanczos kernel k_lanczos_pipe (pure host code, also exported as macb_host_build_slices for the CPU
+// test-suite).  CTA b owns the rows row_start[b] .. row_start[b+1] and their slots rp[row_start[b]] .. rp[row_start[b+1]].
+// Inside a CTA the rows are renumbered by decreasing length ("engine numbering", jrow[engine row] = caller row, jlen = its
+// length); warp w of the CTA owns the engine rows 32 w .. 32 w + 31 -- one SLICE.  A slice is stored like a small ELLPACK
+// matrix padded to its longest row (its first, L_w entries) with a lane stride of kLzSlice = 33 doubles:
+//     position of entry d of engine row t = base_w + d * kLzSlice + (t & 31),      base_w = sum_{w' < w} L_w' * kLzSlice
+// so that the row sums of the kernel need no table of diagonal starts (the jagged-diagonal predecessor paid a dependent
+// shared-memory round trip per eight products for it, measured: 2 400 of a step's 12 500 cycles) and run unpredicated: the
+// padding positions are never written and stay zero.  The rows being sorted, the padding is ~4 %, the odd stride 3 %.
+// jw[b * kLzSliceTab + 2 w] = base_w, [2 w + 1] = L_w;  positions[b] = the CTA's position count.
+// The CTA's SLOTS are stored in column order and carry their position: jcol = column | position << 17 (n < 2^17 - 1, which
+// leaves the all-ones column for "inactive", and < 2^15 positions per CTA).  Which entry d of its row a slot uses is free;
+// with bankfit it is chosen so that the 16 positions a half-warp scatters to fall into different 8-byte banks -- the odd
+// stride is what lets d move the bank.
+void build_slice_layout(int n, const int32_t* rp, const int32_t* col, const int32_t* eid, int ncta, const int* row_start, bool bankfit,
+                        int* jrow, int* jlen, int* jcol, int* jeid, int* jw, int* positions) {
+    std::vector<int> order, inv((size_t)n);   // inv[caller id] = engine id
     for (int b = 0; b < ncta; ++b) {
         const int ra = row_start[b], R = row_start[b + 1] - ra;
         order.resize(R);
@@ -539,75 +542,57 @@ void build_jds_layout(int n, const int32_t* rp, const int32_t* col, const int32_
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
         for (int t = 0; t < R; ++t) {
             jrow[ra + t] = order[t];
+            jlen[ra + t] = rp[order[t] + 1] - rp[order[t]];
             inv[order[t]] = ra + t;
         }
     }
-    std::vector<std::pair<int, int>> key;
-    std::vector<int> tc, te, pos_row, newpos;
+    struct Slot { int col, t, eid; };
+    std::vector<Slot> slots;
     std::vector<std::vector<unsigned char>> used_d;
     for (int b = 0; b < ncta; ++b) {
         const int ra = row_start[b], rb = row_start[b + 1], R = rb - ra;
         const int sa = rp[ra], ns = rp[rb] - sa;
-        cnt.assign((size_t)stride, 0);   // cnt[d] = rows with more than d slots
-        for (int t = 0; t < R; ++t) {
-            const int row = jrow[ra + t], len = rp[row + 1] - rp[row];
-            jlen[ra + t] = len;
-            for (int d = 0; d < len; ++d) cnt[d]++;
-        }
-        int* jdb = jd + (size_t)b * stride;
+        int* tab = jw + (size_t)b * kLzSliceTab;
+        std::fill(tab, tab + kLzSliceTab, 0);
         int acc = 0;
-        for (int d = 0; d < stride; ++d) {
-            jdb[d] = (cnt[d] > 0 || d == 0) ? acc : 0;   // padding entries point at slot 0 (never summed)
-            acc += cnt[d];
+        for (int w = 0; 32 * w < R; ++w) {
+            const int Lw = jlen[ra + 32 * w];
+            tab[2 * w] = acc;
+            tab[2 * w + 1] = Lw;
+            acc += Lw * kLzSlice;
         }
-        for (int t = 0; t < R; ++t) {
-            const int row = jrow[ra + t], s0 = rp[row], len = rp[row + 1] - s0;
-            for (int d = 0; d < len; ++d) {
-                jcol[(size_t)sa + jdb[d] + t] = inv[col[(size_t)s0 + d]];
-                jeid[(size_t)sa + jdb[d] + t] = eid[(size_t)s0 + d];
-            }
-        }
-        if (!sorted) continue;
-        key.resize(ns);
-        for (int q = 0; q < ns; ++q) key[q] = {jcol[(size_t)sa + q], q};
-        std::sort(key.begin(), key.end());
-        tc.resize(ns);
-        te.resize(ns);
-        pos_row.resize(ns);
-        newpos.resize(ns);
+        positions[b] = acc;
+        slots.clear();
         used_d.resize((size_t)R);
         for (int t = 0; t < R; ++t) {
-            const int len = jlen[ra + t];
+            const int row = jrow[ra + t], s0 = rp[row], len = rp[row + 1] - s0;
             used_d[t].assign((size_t)len, 0);
-            for (int d = 0; d < len; ++d) pos_row[(size_t)jdb[d] + t] = t;
+            for (int d = 0; d < len; ++d) slots.push_back({inv[col[(size_t)s0 + d]], t, eid[(size_t)s0 + d]});
         }
+        std::stable_sort(slots.begin(), slots.end(), [](const Slot& x, const Slot& y) { return x.col < y.col; });
         for (int g0 = 0; g0 < ns; g0 += 16) {
             unsigned int banks = 0;
             for (int q = g0; q < std::min(ns, g0 + 16); ++q) {
-                const int t = pos_row[key[q].second];
+                const int t = slots[q].t, base = tab[2 * (t >> 5)] + (t & 31);
                 std::vector<unsigned char>& u = used_d[t];
                 int pick = -1, fallback = -1;
                 for (int d = 0; d < (int)u.size(); ++d) {
                     if (u[d]) continue;
                     if (fallback < 0) fallback = d;
                     if (!bankfit) break;
-                    if (!((banks >> ((jdb[d] + t) & 15)) & 1u)) {
+                    if (!((banks >> ((base + d * kLzSlice) & 15)) & 1u)) {
                         pick = d;
                         break;
                     }
                 }
                 if (pick < 0) pick = fallback;
                 u[pick] = 1;
-                banks |= 1u << ((jdb[pick] + t) & 15);
-                newpos[q] = jdb[pick] + t;
+                const int pos = base + pick * kLzSlice;
+                banks |= 1u << (pos & 15);
+                jcol[(size_t)sa + q] = slots[q].col | (pos << 17);
+                jeid[(size_t)sa + q] = slots[q].eid;
             }
         }
-        for (int q = 0; q < ns; ++q) {
-            tc[q] = key[q].first | (newpos[q] << 17);
-            te[q] = jeid[(size_t)sa + key[q].second];
-        }
-        std::copy(tc.begin(), tc.end(), jcol + sa);
-        std::copy(te.begin(), te.end(), jeid + sa);
     }
 }
 
@@ -702,21 +687,20 @@ void setup_persist(macb_ctx* c) {
                 c->slots_smem = (size_t)max_slots * 12;
             }
             raise_dyn_smem((const void*)k_lanczos_slots, (size_t)(c->slots_smem));
-            // jagged-diagonal layout of k_lanczos_pipe: one chunk per CTA, products + column cache + diagonal starts fit, and the
-            // last ceil(ncta / 32) warps of every CTA free of rows (they poll the exchange records)
-            bool pipe_ok = !getenv("MACB_NO_PIPE") && c->p_ncta <= 256;
+            // sliced layout of k_lanczos_pipe: one chunk per CTA, products + column cache fit, and the last ceil(ncta / 32)
+            // warps of every CTA free of rows (they poll the exchange records)
+            bool pipe_ok = !getenv("MACB_NO_PIPE") && c->p_ncta <= 256 && n < (1 << 17) - 1;
             for (int b = 0; b < c->p_ncta && pipe_ok; ++b) pipe_ok = rs[b + 1] - rs[b] <= (kPWarps - (c->p_ncta + 31) / 32) * 32;
-            const int64_t cap4 = std::max<int64_t>((max_slots + 3) / 4 * 4, kPBlock);   // >= kPBlock: prod[0 + tid] is always addressable
-            const int64_t stride = (maxrow + 8 + 3) / 4 * 4;   // + 8: the row sums read the diagonal starts eight at a time
-            if (pipe_ok && single && c->slots_cache_cols && (size_t)cap4 * 12 + (size_t)stride * 4 <= (size_t)224 * 1024 && !getenv("MACB_NO_JDS") &&
-                !c->h_col.empty()) {
+            const int64_t cap4 = std::max<int64_t>((max_slots + 3) / 4 * 4, 4);
+            if (pipe_ok && single && c->slots_cache_cols && !getenv("MACB_NO_JDS") && !c->h_col.empty()) {
                 const int ncta = c->p_ncta;
                 std::vector<int> jrow((size_t)n), jlen((size_t)n), jcol((size_t)c->nnz), jeid((size_t)c->nnz),
-                    jd((size_t)ncta * stride, 0);
-                // optional: store every CTA's slots in column order (positions of the products packed beside the column)
-                c->jds_sorted = !(getenv("MACB_JDS_SORT") && atoi(getenv("MACB_JDS_SORT")) == 0) && n <= (1 << 17) && cap4 <= (1 << 14);
-                build_jds_layout(n, c->h_rp.data(), c->h_col.data(), c->h_eid.data(), ncta, rs.data(), (int)stride, c->jds_sorted,
-                                 !getenv("MACB_NO_BANKFIT"), jrow.data(), jlen.data(), jcol.data(), jeid.data(), jd.data());
+                    jd((size_t)ncta * kLzSliceTab, 0), positions((size_t)ncta, 0);
+                build_slice_layout(n, c->h_rp.data(), c->h_col.data(), c->h_eid.data(), ncta, rs.data(), !getenv("MACB_NO_BANKFIT"),
+                                   jrow.data(), jlen.data(), jcol.data(), jeid.data(), jd.data(), positions.data());
+                const int64_t pos_cap = std::max<int64_t>((*std::max_element(positions.begin(), positions.end()) + 3) / 4 * 4, 4);
+                pipe_ok = pos_cap < (1 << 15) && (size_t)pos_cap * 8 + (size_t)cap4 * 4 + kLzSliceTab * 4 <= (size_t)224 * 1024;
+                if (pipe_ok) {
                 c->d_jrow = dalloc<int>(n);
                 c->d_jlen = dalloc<int>(n);
                 c->d_jcol = dalloc<int>(c->nnz);
@@ -730,10 +714,9 @@ void setup_persist(macb_ctx* c) {
                 CK(cudaMemcpyAsync(c->d_jeid, jeid.data(), sizeof(int) * c->nnz, cudaMemcpyHostToDevice, c->stream));
                 CK(cudaMemcpyAsync(c->d_jd, jd.data(), sizeof(int) * jd.size(), cudaMemcpyHostToDevice, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
-                c->jd_stride = (int)stride;
-                c->slots_prod_cap = (int)cap4;
-                c->slots_smem = (size_t)cap4 * 12 + (size_t)stride * 4;
-                c->pipe_smem = c->slots_smem;
+                c->pipe_pos_cap = (int)pos_cap;
+                c->pipe_slot_cap = (int)cap4;
+                c->pipe_smem = (size_t)pos_cap * 8 + (size_t)cap4 * 4 + kLzSliceTab * 4;
                 c->pipe = true;
                 {   // gathers in flight per thread: the batch size whose last batch of a step is fullest (see kernels.cuh)
                     const double pt = (double)max_slots / (double)kPBlock;
@@ -755,11 +738,12 @@ void setup_persist(macb_ctx* c) {
                 alloc_device_rr(c);
                 // the Rayleigh-Ritz CTA keeps T_k (seven arrays) in the launch's dynamic shared memory while it fits
                 if (c->dev_rr) c->pipe_smem = std::max(c->pipe_smem, rr_smem_bytes(c));
-#define MACB_PIPE_SMEM(VB_)                                                \
-    raise_dyn_smem((const void*)k_lanczos_pipe<false, VB_>, c->pipe_smem); \
-    raise_dyn_smem((const void*)k_lanczos_pipe<true, VB_>, c->pipe_smem);
-                MACB_PIPE_SMEM(3) MACB_PIPE_SMEM(4) MACB_PIPE_SMEM(5) MACB_PIPE_SMEM(6) MACB_PIPE_SMEM(7) MACB_PIPE_SMEM(8)
-#undef MACB_PIPE_SMEM
+                raise_dyn_smem((const void*)k_lanczos_pipe<3>, c->pipe_smem);
+                raise_dyn_smem((const void*)k_lanczos_pipe<4>, c->pipe_smem);
+                raise_dyn_smem((const void*)k_lanczos_pipe<5>, c->pipe_smem);
+                raise_dyn_smem((const void*)k_lanczos_pipe<6>, c->pipe_smem);
+                raise_dyn_smem((const void*)k_lanczos_pipe<7>, c->pipe_smem);
+                raise_dyn_smem((const void*)k_lanczos_pipe<8>, c->pipe_smem);
                 c->persist_v = 5;
                 if (!getenv("MACB_NO_L2PIN")) {
                     // keep the weights the Lanczos kernel streams every step (8 bytes per slot) in the persisting part of L2
@@ -791,11 +775,12 @@ void setup_persist(macb_ctx* c) {
                         cudaGetLastError();
                     }
                 }
-                if (c->have_x) {   // L(x) was assembled before the engine existed: fill the jagged copy of the weights once
+                if (c->have_x) {   // L(x) was assembled before the engine existed: fill the engine's copy of the weights once
                     k_assemble_jds<<<c->grid_for(c->nnz), kBlock, 0, c->stream>>>(c->nnz, c->d_jeid, c->d_ew, c->d_jval);
                     CK(cudaGetLastError());
                     c->c_launches++;
                 }
+                }   // pipe_ok (positions fit)
             }
         }
     }
@@ -1372,19 +1357,26 @@ int macb_host_build_pattern(int32_t n, int64_t nf, const int32_t* fi, const int3
     }
 }
 
-int macb_host_build_jds(int32_t n, const int32_t* rp, const int32_t* col, const int32_t* eid, int32_t ncta, const int32_t* row_start,
-                        int32_t stride, int sorted, int bankfit, int32_t* jrow, int32_t* jlen, int32_t* jcol, int32_t* jeid, int32_t* jd) {
-    if (n < 0 || ncta < 1 || !rp || !row_start || !jrow || !jlen || !jcol || !jeid || !jd) return MACB_ERR_ARG;
-    if (sorted && n > (1 << 17)) return MACB_ERR_ARG;
+int macb_host_build_slices(int32_t n, const int32_t* rp, const int32_t* col, const int32_t* eid, int32_t ncta, const int32_t* row_start,
+                           int bankfit, int32_t* jrow, int32_t* jlen, int32_t* jcol, int32_t* jeid, int32_t* jw, int32_t* positions) {
+    if (n < 0 || ncta < 1 || !rp || !row_start || !jrow || !jlen || !jcol || !jeid || !jw || !positions) return MACB_ERR_ARG;
+    if (n >= (1 << 17) - 1) return MACB_ERR_ARG;
     for (int b = 0; b < ncta; ++b) {
         const int R = row_start[b + 1] - row_start[b];
-        const int64_t ns = (int64_t)rp[row_start[b + 1]] - rp[row_start[b]];
-        if (R < 0 || (sorted && ns > (1 << 14))) return MACB_ERR_ARG;
-        for (int r = row_start[b]; r < row_start[b + 1]; ++r)
-            if (rp[r + 1] - rp[r] + 1 > stride) return MACB_ERR_ARG;
+        if (R < 0 || R > 32 * (kLzSliceTab / 2)) return MACB_ERR_ARG;
+        int64_t pos = 0;
+        for (int r = row_start[b]; r < row_start[b + 1]; ++r) pos = std::max<int64_t>(pos, rp[r + 1] - rp[r]);
+        if (pos * kLzSlice * ((R + 31) / 32) >= (1 << 15)) {   // cheap upper bound first, exact count below
+            std::vector<int> lens;
+            for (int r = row_start[b]; r < row_start[b + 1]; ++r) lens.push_back(rp[r + 1] - rp[r]);
+            std::sort(lens.begin(), lens.end(), std::greater<int>());
+            int64_t exact = 0;
+            for (size_t t = 0; t < lens.size(); t += 32) exact += (int64_t)lens[t] * kLzSlice;
+            if (exact >= (1 << 15)) return MACB_ERR_ARG;
+        }
     }
     try {
-        build_jds_layout(n, rp, col, eid, ncta, row_start, stride, sorted != 0, bankfit != 0, jrow, jlen, jcol, jeid, jd);
+        build_slice_layout(n, rp, col, eid, ncta, row_start, bankfit != 0, jrow, jlen, jcol, jeid, jw, positions);
     } catch (const std::bad_alloc&) {
         return MACB_ERR_NOMEM;
     }

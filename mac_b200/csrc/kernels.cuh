@@ -880,14 +880,15 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
 //  * the first batch of gathers of step j+1 is issued straight after the barrier of step j, BEFORE the CTA fetches
 //    the 148 partial-sum records and runs the (long-latency, double-precision) coefficient chain: the gathers need
 //    only addresses, the coefficients are needed when the products are formed.
+constexpr int kLzSlice = 33;      // lane stride of a slice (doubles): odd, so that the entry index moves the shared-memory bank
+constexpr int kLzSliceTab = 64;   // ints per CTA in the slice table: (base, length) of up to 32 slices
 struct LzJdsArgs {
     const int* row_start;   // [ncta + 1] rows of CTA b (<= kPBlock of them), in the ENGINE's node numbering
-    const int* jlen;        // [n]   number of slots of engine row i
-    const int* jcol;        // [nnz] column (engine numbering) of every slot, jagged-diagonal order inside a CTA's slot range
+    const int* jcol;        // [nnz] engine column | product position << 17 of every slot, column order inside a CTA's slot range
     const double* jval;     // [nnz] weight of every slot, same order (k_assemble_jds)
-    const int* jd;          // [ncta * jd_stride] first CTA-local slot of diagonal d
-    int jd_stride;
-    int prod_cap;           // slots reserved for the product buffer; the column cache and jd follow
+    const int* jw;          // [ncta * kLzSliceTab] slice table: (first position, entries per row) of warp w's 32 rows
+    int pos_cap;            // product positions reserved in shared memory (doubles); the column cache and the slice table follow
+    int slot_cap;           // slots reserved for the column cache (ints)
     double* xrec;           // [2][ncta][ncta][4] inboxes of the all-to-all barrier, NaN = empty (k_lz_persist_init)
     const double* diag;     // [n] weighted degrees, caller numbering 
     const int* perm;        // [n] engine -> caller numbering
@@ -963,11 +964,13 @@ __device__ __forceinline__ double ld_f64_relaxed_if(const double* p, bool pred, 
     return v;
 }
 
-template <bool SORTED, int VB>
+// One word per slot in the shared-memory column cache: engine column (17 bits; all ones = the slot's weight is zero in this
+// launch, nothing to gather or store) | position of its product << 17 (15 bits).
+constexpr int kLzColMask = 0x1ffff;
+template <int VB>
 __device__ __forceinline__ void lz_gather_products_tagged(const double* __restrict__ U, const int* __restrict__ scol,
                                                           const double* __restrict__ jval, int ns, int tid, int tag,
                                                           double* __restrict__ prod, int* give_up) {
-    constexpr int CM = SORTED ? 0x1ffff : 0x7fffffff;
     const double ok_zero = __longlong_as_double((long long)tag);   // what an unissued gather "returns": +0 with a valid tag
     for (int b0 = tid; b0 < ns; b0 += VB * kPBlock) {
         int c[VB];
@@ -975,48 +978,50 @@ __device__ __forceinline__ void lz_gather_products_tagged(const double* __restri
 #pragma unroll
         for (int q = 0; q < VB; ++q) {
             const int b = b0 + q * kPBlock;
-            c[q] = (b < ns) ? scol[b] : (int)0x80000000;
+            c[q] = (b < ns) ? scol[b] : kLzColMask;
         }
 #pragma unroll
-        for (int q = 0; q < VB; ++q) v[q] = ld_f64_relaxed_if(U + (c[q] & CM), c[q] >= 0, ok_zero);
+        for (int q = 0; q < VB; ++q) v[q] = ld_f64_relaxed_if(U + (c[q] & kLzColMask), (c[q] & kLzColMask) != kLzColMask, ok_zero);
         // the weights of the whole batch are requested up front as well: loaded one by one next to their use they form a
         // chain of VB dependent L2 latencies per batch
 #pragma unroll
-        for (int q = 0; q < VB; ++q) wq[q] = (c[q] >= 0) ? ld_stream(jval + b0 + q * kPBlock) : 0.0;
+        for (int q = 0; q < VB; ++q) wq[q] = ((c[q] & kLzColMask) != kLzColMask) ? ld_stream(jval + b0 + q * kPBlock) : 0.0;
 #pragma unroll
         for (int q = 0; q < VB; ++q) {
-            const int b = b0 + q * kPBlock;
             if (!lz_tag_ok(v[q], tag)) {   // producer has not written yet: gather again (bounded: never hang the device)
                 unsigned int tries = 0;
                 do {
                     __nanosleep(100);   // the producer is still in its row sums: do not fill the memory pipe with polls
-                    v[q] = ld_f64_relaxed_if(U + (c[q] & CM), true, ok_zero);
+                    v[q] = ld_f64_relaxed_if(U + (c[q] & kLzColMask), true, ok_zero);
                 } while (!lz_tag_ok(v[q], tag) && ++tries < (1u << 16));
                 if (!lz_tag_ok(v[q], tag)) *give_up = 1;
             }
-            if (b < ns) prod[SORTED ? ((c[q] >> 17) & 0x3fff) : b] = wq[q] * v[q];
+            // inactive slots store nothing: their positions keep the zero written when the launch began
+            if ((c[q] & kLzColMask) != kLzColMask) prod[(unsigned int)c[q] >> 17] = wq[q] * v[q];
         }
     }
 }
 
-// sum of the products of row `tid` along the jagged diagonals d0 <= d < len (d0 a multiple of 8; eight per trip, predicated
-// tail; jd is padded by 8 entries)
-__device__ __forceinline__ double lz_row_sum(const double* __restrict__ prod, const int* __restrict__ sjd, int len, int tid, int d0 = 0) {
-    const double* __restrict__ pt = prod + tid;
+// sum of entries d0 <= d < d1 of one row of a slice: p points at entry 0 of the lane's row, entries are kLzSlice doubles apart.
+// All addresses are known up front (no table of diagonal starts between the loads), all lanes of the warp run the same trip
+// count (the slice is padded with zeros to its longest row), nothing is predicated.
+__device__ __forceinline__ double lz_slice_sum(const double* __restrict__ p, int d0, int d1) {
+    const double* __restrict__ q = p + d0 * kLzSlice;
+    int n = d1 - d0;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
-    for (int d = d0; d < len; d += 8) {
-        const int4 o = *reinterpret_cast<const int4*>(sjd + d);
-        const int4 p = *reinterpret_cast<const int4*>(sjd + d + 4);
-        const int r = len - d;
-        a0 += pt[o.x];
-        a1 += (r > 1) ? pt[o.y] : 0.0;
-        a2 += (r > 2) ? pt[o.z] : 0.0;
-        a3 += (r > 3) ? pt[o.w] : 0.0;
-        a4 += (r > 4) ? pt[p.x] : 0.0;
-        a5 += (r > 5) ? pt[p.y] : 0.0;
-        a6 += (r > 6) ? pt[p.z] : 0.0;
-        a7 += (r > 7) ? pt[p.w] : 0.0;
+    for (; n >= 8; n -= 8, q += 8 * kLzSlice) {
+        a0 += q[0]; a1 += q[kLzSlice]; a2 += q[2 * kLzSlice]; a3 += q[3 * kLzSlice];
+        a4 += q[4 * kLzSlice]; a5 += q[5 * kLzSlice]; a6 += q[6 * kLzSlice]; a7 += q[7 * kLzSlice];
     }
+    if (n & 4) {
+        a0 += q[0]; a1 += q[kLzSlice]; a2 += q[2 * kLzSlice]; a3 += q[3 * kLzSlice];
+        q += 4 * kLzSlice;
+    }
+    if (n & 2) {
+        a4 += q[0]; a5 += q[kLzSlice];
+        q += 2 * kLzSlice;
+    }
+    if (n & 1) a6 += q[0];
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
@@ -1720,7 +1725,7 @@ struct LzPipeShared {
 
 // Host contract (setup_persist): every CTA has at most (kPWarps - ceil(ncta / 32)) * 32 rows, so that the last ceil(ncta / 32)
 // warps own no rows and can act as the polling warps.
-template <bool SORTED, int VB>
+template <int VB>
 __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, LzJdsArgs J, LzPipeArgs P, RrArgs R) {
     if (blockIdx.x == (unsigned int)a.ncta) {   // the extra CTA of the launch: on-device Rayleigh-Ritz / stop decision
         extern __shared__ double rr_smem[];
@@ -1730,21 +1735,20 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
     extern __shared__ double prod[];
     __shared__ double sm[4 * kPWarps];
     __shared__ LzPipeShared sh;
-    __shared__ unsigned short slen[kPBlock];   // row lengths (a global load here would put an L2 round trip -- 2 500 cycles under
-                                               // this kernel's own load, measured -- in front of every row sum)
-    __shared__ double hsum[256];          // partial row sums of the helper threads (long rows are split in two)
+    __shared__ double hsum[256];          // partial row sums of the helper warps (the longest slices are split in two)
     __shared__ int stop_in;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = (int)threadIdx.x;
-    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.prod_cap);
-    int* __restrict__ sjd = scol + J.prod_cap;
+    int* __restrict__ scol = reinterpret_cast<int*>(prod + J.pos_cap);
+    int* __restrict__ sjw = scol + J.slot_cap;
     const int ra = J.row_start[blockIdx.x], rb = J.row_start[blockIdx.x + 1];
     const int sa = a.rp[ra], ns = a.rp[rb] - sa;
     const bool has_row = tid < rb - ra;
     const int row = ra + tid;
     const double* __restrict__ jval = J.jval + sa;
-    for (int i = tid; i < ns; i += kPBlock)
-        scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? (int)0x80000000 : 0);
-    for (int i = tid; i < J.jd_stride; i += kPBlock) sjd[i] = J.jd[(size_t)blockIdx.x * J.jd_stride + i];
+    // column cache: a slot whose weight is zero in this launch (a candidate edge outside the support) is marked inactive
+    for (int i = tid; i < ns; i += kPBlock) scol[i] = ld_nc(J.jcol + sa + i) | ((ld_nc(jval + i) == 0.0) ? kLzColMask : 0);
+    for (int i = tid; i < J.pos_cap; i += kPBlock) prod[i] = 0.0;   // padding and inactive positions are never written again
+    if (tid < kLzSliceTab) sjw[tid] = J.jw[(size_t)blockIdx.x * kLzSliceTab + tid];
     int phase = a.st->phase;
     int cur = a.st->cur;
     if (tid == 0) {
@@ -1759,18 +1763,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
     const int rows_warps = (rb - ra + 31) >> 5;
     const int poll_warps = ((int)ncta + 31) >> 5;
     const int first_poll_warp = kPWarps - poll_warps;
-    // Long rows are split in two.  The rows are numbered by decreasing length, so row/thread 0 has the longest (twice the mean
-    // on an Erdos-Renyi graph) and its row sum, a chain of dependent shared-memory round trips, is what the whole CTA waits for
-    // at the end of pass 2.  The warps that neither own rows nor poll ("helpers", nhelp threads) take the diagonals d >= split
-    // of rows 0 .. nhelp-1; split = the length of row nhelp rounded up to 8, at least half the longest row.
-    const int nhelp = max(0, min(min((first_poll_warp - rows_warps) * 32, 256), rb - ra));
-    int split = 1 << 30;
-    if (nhelp > 0) {
-        const int lmax = ld_nc(J.jlen + ra), lcut = ld_nc(J.jlen + ra + min(nhelp, rb - ra - 1));
-        split = max((lcut + 7) & ~7, (((lmax + 1) >> 1) + 7) & ~7);
-    }
-    const int helper_row = tid - rows_warps * 32;   // >= 0 and < nhelp: this thread helps row `helper_row`
-    slen[tid] = (unsigned short)(has_row ? ld_nc(J.jlen + row) : 0);
+    // The longest slices are split in two.  The rows are numbered by decreasing length, so warp 0 has the longest (twice the
+    // mean on an Erdos-Renyi graph) and the whole CTA waits for its row sums at the end of pass 2.  The warps that neither own
+    // rows nor poll ("helpers", nhw of them) take the second half of the entries of slices 0 .. nhw-1.
+    const int nhw = max(0, min(min(first_poll_warp - rows_warps, rows_warps), 8));
     // ONE base pointer for all per-row state in L2, rows of `ld` doubles: [0], [1] the two z buffers (= a.sect[0], a.sect[1]),
     // [2], [3] u_j / u_{j-1} alternating like them (the basis is written with evict-first stores: reading it back is a DRAM
     // round trip, measured), [4] the diagonal of L' = L - sigma I in engine order.  (Never index a.sect[] with a run-time value:
@@ -1802,7 +1798,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
         const int tag = (phase >> 1) & 1, tag_next = ((phase + 1) >> 1) & 1;
 #ifdef MACB_PTIMING
         const long long t_start = clock64();
-        long long t_p1 = 0, t_rows = 0, t_bar = 0, tb0 = 0, tb1 = 0;
+        long long t_p1 = 0, t_rows = 0, t_bar = 0, tb0 = 0, tb1 = 0, tu1 = 0, tu2 = 0, tu3 = 0;
 #endif
         // ---- records of this phase: the last warp finishes the block sums and pushes them into every CTA's inbox
         if (warp == kPWarps - 1) {
@@ -1836,23 +1832,39 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
             for (unsigned int b = lane; b < ncta; b += 32) st_sector(box + ((size_t)b * ncta + blockIdx.x) * 4, q0, q1, q2, q3);
         }
         // ---- pass 1: products of the CTA's slots with the gathered z_phase
-        lz_gather_products_tagged<SORTED, VB>(Z, scol, jval, ns, tid, tag, prod, &sh.give_up);
+        lz_gather_products_tagged<VB>(Z, scol, jval, ns, tid, tag, prod, &sh.give_up);
+        // The loads of the tail (the row's state / the polling lane's record) are issued before the barrier that ends pass 1.
+        // (Issued one batch of gathers earlier they change nothing -- measured: the tail is bound by issue slots, not by them.)
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, r4 = 0.0;
+        const bool polling = warp >= first_poll_warp;
+        const unsigned int pb = (unsigned int)(tid - first_poll_warp * 32);
+        const double* const mine = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4 + (size_t)blockIdx.x * ncta * 4;
+        if (polling) {
+            r0 = __longlong_as_double((long long)tag);
+            if (pb < ncta)
+                asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(mine + (size_t)pb * 4) : "memory");
+        } else if (has_row) {
+            const double* __restrict__ Sr = LZS + row;
+            r4 = __ldcg(Sr + 4 * LZLD);
+            r0 = __ldcg(Sr + (2 + cur) * LZLD);
+            r1 = __ldcg(Sr + cur * LZLD);
+            if (phase > 0) {
+                r2 = __ldcg(Sr + (3 - cur) * LZLD);
+                r3 = __ldcg(Sr + (cur ^ 1) * LZLD);   // the buffer about to be overwritten still holds z_{phase-1}
+            }
+        }
 
         // From here to the update the polling warps and the row warps run DIFFERENT code between the same two CTA barriers,
         // so that what a row thread keeps in registers (its state, requested from L2 before the first barrier) is not live
         // across the register-hungry polling / coefficient code: inlined into one path the allocator spills it to local memory.
         // Everything needed from L2 is requested BEFORE the barrier that ends pass 1: an L2 round trip costs ~2 500 cycles
         // while the other SMs are gathering -- as long as the row sums and the update together.
-        if (warp >= first_poll_warp) {
+        if (polling) {
             // ---- polling warps: this lane's record of the exchange (pushed a whole SpMV ago by everybody); one record per lane
             // = ONE L2 round trip.  The last lane-0 then runs the (long, double-precision) coefficient chain for the whole CTA
             // while the others sum their rows: nothing of the reduction is left on the critical path.
-            const double* const mine = J.xrec + (size_t)(phase & 1) * ncta * ncta * 4 + (size_t)blockIdx.x * ncta * 4;
-            const unsigned int pb = (unsigned int)(tid - first_poll_warp * 32);
-            double y0 = __longlong_as_double((long long)tag), y1 = 0.0, y2 = 0.0, y3 = 0.0;
-            if (pb < ncta)
-                asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-                             : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3) : "l"(mine + (size_t)pb * 4) : "memory");
+            double y0 = r0, y1 = r1, y2 = r2, y3 = r3;
             LZ_BAR(2);
 #ifdef MACB_PTIMING
             tb0 = clock64();
@@ -1893,30 +1905,22 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
         } else {
             // ---- row warps (and helpers): the row's state from L2 (u_j, u_{j-1}, z_j, z_{j-1}, diagonal; not carried in
             // registers across the gather loop, where it would be spilled), the row sums, the update
-            double su = 0.0, sq = 0.0, sz = 0.0, szp = 0.0, qr = 0.0, od = 0.0;
-            if (has_row) {
-                const double* __restrict__ Sr = LZS + row;
-                od = __ldcg(Sr + 4 * LZLD);
-                su = __ldcg(Sr + (2 + cur) * LZLD);
-                sz = __ldcg(Sr + cur * LZLD);
-                if (phase > 0) {
-                    sq = __ldcg(Sr + (3 - cur) * LZLD);
-                    szp = __ldcg(Sr + (cur ^ 1) * LZLD);   // the buffer about to be overwritten still holds z_{phase-1}
-                }
-            }
+            const double su = r0, sz = r1, sq = r2, szp = r3, od = r4;
+            double qr = 0.0;
             LZ_BAR(2);
 #ifdef MACB_PTIMING
             t_p1 = clock64();
 #endif
-            // ---- pass 2: the products of the CTA's rows, summed along the jagged diagonals
+            // ---- pass 2: the products of the CTA's rows, summed along their slices
             bool helped = false;
-            if (has_row) {
-                const int len = slen[tid];
-                qr = lz_row_sum(prod, sjd, min(len, split), tid);
-                helped = (tid < nhelp) && (len > split);
-            } else if (helper_row >= 0 && helper_row < nhelp) {
-                const int len = slen[helper_row];
-                if (len > split) hsum[helper_row] = lz_row_sum(prod, sjd, len, helper_row, split);
+            if (warp < rows_warps) {
+                const int2 wl = *reinterpret_cast<const int2*>(sjw + 2 * warp);   // first position, entries per row
+                helped = warp < nhw;
+                qr = lz_slice_sum(prod + wl.x + lane, 0, helped ? ((wl.y + 1) >> 1) : wl.y);
+            } else if (warp - rows_warps < nhw) {
+                const int hw = warp - rows_warps;
+                const int2 wl = *reinterpret_cast<const int2*>(sjw + 2 * hw);
+                hsum[hw * 32 + lane] = lz_slice_sum(prod + wl.x + lane, (wl.y + 1) >> 1, wl.y);
             }
 #ifdef MACB_PTIMING
             t_rows = clock64();
@@ -1933,14 +1937,23 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
                 qr = fma(od, sz, -qr);   // (L' z_phase)[row]
                 const double un = fma(k1, sz, fma(k2, su, k3 * sq)) + k4;
                 const double zn = lz_tagged(fma(k1, qr, fma(k2, sz, k3 * szp)) - sh.sigma * k4, tag_next);
+#ifdef MACB_PTIMING
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(tu1) : "d"(zn), "d"(un));
+#endif
                 __stcg(LZS + (cur ^ 1) * LZLD + row, zn);
                 __stcg(LZS + (3 - cur) * LZLD + row, un);
                 __stcs(a.basis + (size_t)(phase + 1) * a.ld + row, un);   // streaming: the basis must not push the matrix out of L2
                 p1 = un * zn; p2 = zn; p3 = un * un; p4 = un;
+#ifdef MACB_PTIMING
+                tu2 = clock64();
+#endif
             }
             if (warp < rows_warps) {
                 const double r = warp_sum4(p1, p2, p3, p4, lane);
                 if ((lane & 7) == 0) sm[(lane >> 3) * kPWarps + warp] = r;
+#ifdef MACB_PTIMING
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(tu3) : "d"(r));
+#endif
             }
             if (blockIdx.x == 0 && tid == 0) {
                 const double alpha = sh.coef[4] + sh.sigma, beta = sh.coef[5];
@@ -1953,8 +1966,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
 #ifdef MACB_PTIMING
         if ((tid == 0 || tid == kPBlock - 32) && a.timing && it < 64) {
             long long* t = a.timing + ((size_t)it * a.ncta + blockIdx.x) * 8;
-            if (tid == 0) { t[0] = t_start; t[1] = t_p1; t[2] = t_rows; t[6] = t_bar; t[7] = clock64(); }
-            else { t[3] = tb0; t[4] = tb1; t[5] = tb1; }
+            if (tid == 0) { t[0] = t_start; t[1] = t_p1; t[2] = t_rows; t[6] = t_bar; t[7] = clock64(); t[3] = tu1; t[4] = tu2; t[5] = tu3; }
+            (void)tb0; (void)tb1;
         }
 #endif
         cur ^= 1;

@@ -173,7 +173,7 @@ def test_warm_start_reaches_the_same_pair():
 
 
 @pytest.mark.parametrize("env", [{"MACB_HOST_RR": "1"}, {"MACB_NO_PIPE": "1"}, {"MACB_PERSIST_V": "1"}, {"MACB_NO_JDS": "1"},
-                                 {"MACB_JDS_SORT": "0"}, {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
+                                 {"MACB_NO_JDS": "1", "MACB_NO_COLCACHE": "1"},
                                  {"MACB_PERSIST_V": "1", "MACB_HOST_RR": "1"}])
 def test_lanczos_engines_agree(monkeypatch, env):
     """The default engine (k_lanczos_pipe: pipelined shifted Lanczos on the jagged-diagonal layout, stop decision by the

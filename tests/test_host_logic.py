@@ -190,71 +190,76 @@ def test_synthetic_generators_are_deterministic():
     assert k == 4000 and x0.sum() == 4000 and len(fixed[0]) == n - 1
 
 
-@pytest.mark.parametrize("sorted_slots,bankfit", [(False, False), (True, False), (True, True)])
-def test_jagged_diagonal_layout_invariants(sorted_slots, bankfit):
-    """The layout k_lanczos_pipe reads (csrc/api.cu build_jds_layout), checked on the host: engine
-    numbering is a within-CTA permutation by decreasing length, every row owns exactly one position per diagonal
-    jd[d] + t, positions tile the CTA's slot range, and every slot still carries its (row, column, edge) triple."""
+def _check_slices(n, rp, col, eid, row_start, bankfit):
+    """Invariants of the layout k_lanczos_pipe reads (csrc/api.cu build_slice_layout).  Returns (bank conflicts, groups)."""
     from mac_b200 import _lib
-    fixed, cand, n = synth.chain_plus_random(700, 5000, seed=11, weighted=True)
-    rp, col, eid = _lib.host_build_pattern(n, fixed[0], fixed[1], cand[0], cand[1])
-    row_start = np.array([0, 150, 151, 400, 700], dtype=np.int32)      # four CTAs, one with a single row
+    S = _lib.SLICE_STRIDE
     lens = np.diff(rp)
-    stride = ((lens.max() + 8 + 3) // 4) * 4
-    jrow, jlen, jcol, jeid, jd = _lib.host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots, bankfit)
+    jrow, jlen, jcol, jeid, jw, positions = _lib.host_build_slices(n, rp, col, eid, row_start, bankfit)
     assert sorted(jrow.tolist()) == list(range(n))
-    inv = np.empty(n, dtype=np.int64)
-    inv[jrow] = np.arange(n)
     conflicts = groups = 0
     for b in range(len(row_start) - 1):
-        ra, rb = row_start[b], row_start[b + 1]
-        sa, ns = rp[ra], rp[rb] - rp[ra]
+        ra, rb = int(row_start[b]), int(row_start[b + 1])
+        R = rb - ra
+        sa, ns = int(rp[ra]), int(rp[rb] - rp[ra])
         assert sorted(jrow[ra:rb].tolist()) == list(range(ra, rb))           # permutation inside the CTA
         assert np.array_equal(jlen[ra:rb], lens[jrow[ra:rb]])
         assert np.all(np.diff(jlen[ra:rb]) <= 0)                              # decreasing length
-        cnt = np.array([(jlen[ra:rb] > d).sum() for d in range(stride)])
-        assert np.array_equal(jd[b][cnt > 0], np.concatenate([[0], np.cumsum(cnt)[:-1]])[cnt > 0])
-        words = jcol[sa:sa + ns]
-        if sorted_slots:
-            cols, pos = words & 0x1ffff, (words >> 17) & 0x3fff
-            assert np.all(np.diff(cols) >= 0)                                 # column order
-            for g0 in range(0, ns, 16):
-                grp = pos[g0:g0 + 16] & 15
-                groups += 1
-                conflicts += len(grp) - len(set(grp.tolist()))
-        else:
-            cols, pos = words, np.arange(ns)
-        assert sorted(pos.tolist()) == list(range(ns))                        # positions tile the slot range
-        # position -> (engine row t, diagonal d): the d with jd[d] <= pos < jd[d] + cnt[d]
-        starts = jd[b][:int((cnt > 0).sum())]
-        d_of = np.searchsorted(starts, pos, side="right") - 1
-        t_of = pos - starts[d_of]
-        assert np.all(t_of < cnt[d_of])
+        # slice table: warp w owns engine rows 32 w .. 32 w + 31, padded to its first (longest) row
+        nw = (R + 31) // 32
+        Lw = np.array([jlen[ra + 32 * w] for w in range(nw)], dtype=np.int64)
+        base = np.concatenate([[0], np.cumsum(Lw * S)])[:nw].astype(np.int64)
+        assert np.array_equal(jw[b][0:2 * nw:2], base) and np.array_equal(jw[b][1:2 * nw:2], Lw)
+        assert positions[b] == int((Lw * S).sum())
+        if ns == 0:
+            continue
+        words = jcol[sa:sa + ns].astype(np.int64) & 0xffffffff
+        cols, pos = words & 0x1ffff, words >> 17
+        assert np.all(np.diff(cols) >= 0)                                     # column order
+        assert np.all(cols != 0x1ffff)                                        # all ones is reserved for "inactive"
+        assert len(set(pos.tolist())) == ns and pos.max() < positions[b]      # every slot its own position
+        for g0 in range(0, ns, 16):
+            grp = pos[g0:g0 + 16] & 15
+            groups += 1
+            conflicts += len(grp) - len(set(grp.tolist()))
+        # position -> (slice w, entry d, lane l) -> engine row t.  Slices without entries share their base with the next one.
+        ends = base + Lw * S
+        w_of = np.searchsorted(ends, pos, side="right")
+        off = pos - base[w_of]
+        d_of, l_of = off // S, off % S
+        assert np.all(l_of < 32)
+        t_of = 32 * w_of + l_of
+        assert np.all(t_of < R) and np.all(d_of < jlen[ra + t_of])            # inside the row, never in the padding
         rows = jrow[ra + t_of]                                                # caller row of every slot
         triples = sorted(zip(rows.tolist(), jrow[cols].tolist(), jeid[sa:sa + ns].tolist()))
         ref = sorted((r, int(col[s]), int(eid[s])) for r in range(ra, rb) for s in range(rp[r], rp[r + 1]))
         assert triples == ref
-        # every row uses each of its diagonals exactly once
+        # every row uses each of its entries exactly once
         per_row = {}
         for t, d in zip(t_of.tolist(), d_of.tolist()):
             per_row.setdefault(t, []).append(d)
         assert all(sorted(ds) == list(range(jlen[ra + t])) for t, ds in per_row.items())
-    if sorted_slots and bankfit:
-        # first fit removes most of the bank collisions a position-by-CSR-order placement has (5.6 -> 1.4 per group here)
-        _, _, jcol0, _, _ = _lib.host_build_jds(n, rp, col, eid, row_start, stride, True, False)
-        base = 0
-        for b in range(len(row_start) - 1):
-            sa, ns = rp[row_start[b]], rp[row_start[b + 1]] - rp[row_start[b]]
-            pos0 = (jcol0[sa:sa + ns] >> 17) & 0x3fff
-            for g0 in range(0, ns, 16):
-                grp = pos0[g0:g0 + 16] & 15
-                base += len(grp) - len(set(grp.tolist()))
+    return conflicts, groups
+
+
+@pytest.mark.parametrize("bankfit", [False, True])
+def test_slice_layout_invariants(bankfit):
+    """Engine numbering is a within-CTA permutation by decreasing length, every row owns exactly one position per entry,
+    positions never fall into the padding, and every slot still carries its (row, column, edge) triple."""
+    from mac_b200 import _lib
+    fixed, cand, n = synth.chain_plus_random(700, 5000, seed=11, weighted=True)
+    rp, col, eid = _lib.host_build_pattern(n, fixed[0], fixed[1], cand[0], cand[1])
+    row_start = np.array([0, 150, 151, 400, 700], dtype=np.int32)      # four CTAs, one with a single row
+    conflicts, groups = _check_slices(n, rp, col, eid, row_start, bankfit)
+    if bankfit:
+        # first fit removes most of the bank collisions a first-free-entry placement has
+        base, _ = _check_slices(n, rp, col, eid, row_start, False)
         assert conflicts < 0.4 * base
 
 
-def test_jagged_diagonal_layout_on_ragged_random_graphs():
+def test_slice_layout_on_ragged_random_graphs():
     """Same invariants on many small ragged inputs: isolated nodes (rows without slots), CTAs without rows, CTAs with a
-    single row, hubs, both slot orders.  Exercises the corner cases the GPU tests cannot enumerate."""
+    single row, hubs.  Exercises the corner cases the GPU tests cannot enumerate."""
     from mac_b200 import _lib
     rng = np.random.default_rng(2024)
     for trial in range(60):
@@ -270,33 +275,9 @@ def test_jagged_diagonal_layout_on_ragged_random_graphs():
             hub = np.full(n // 2, 3, dtype=np.int32)
             ci = np.concatenate([ci, hub]); cj = np.concatenate([cj, rng.integers(0, n, size=len(hub)).astype(np.int32)])
         rp, col, eid = _lib.host_build_pattern(n, fi, fj, ci, cj)
-        lens = np.diff(rp)
-        stride = int(((lens.max(initial=0) + 8 + 3) // 4) * 4)
         cuts = np.sort(rng.integers(0, n + 1, size=int(rng.integers(0, 5))))
         row_start = np.concatenate([[0], cuts, [n]]).astype(np.int32)          # may contain empty CTAs
-        for sorted_slots in (False, True):
-            jrow, jlen, jcol, jeid, jd = _lib.host_build_jds(n, rp, col, eid, row_start, stride, sorted_slots, True)
-            assert sorted(jrow.tolist()) == list(range(n))
-            for b in range(len(row_start) - 1):
-                ra, rb = int(row_start[b]), int(row_start[b + 1])
-                sa, ns = int(rp[ra]), int(rp[rb] - rp[ra])
-                assert sorted(jrow[ra:rb].tolist()) == list(range(ra, rb))
-                assert np.array_equal(jlen[ra:rb], lens[jrow[ra:rb]])
-                assert np.all(np.diff(jlen[ra:rb]) <= 0)
-                if ns == 0:
-                    continue
-                words = jcol[sa:sa + ns]
-                cols, pos = ((words & 0x1ffff, (words >> 17) & 0x3fff) if sorted_slots else (words, np.arange(ns)))
-                assert sorted(pos.tolist()) == list(range(ns))
-                cnt = np.array([(jlen[ra:rb] > d).sum() for d in range(stride)])
-                starts = jd[b][:int((cnt > 0).sum())]
-                d_of = np.searchsorted(starts, pos, side="right") - 1
-                t_of = pos - starts[d_of]
-                assert np.all(t_of < cnt[d_of])
-                rows = jrow[ra + t_of]
-                triples = sorted(zip(rows.tolist(), jrow[cols].tolist(), jeid[sa:sa + ns].tolist()))
-                ref = sorted((r, int(col[s_]), int(eid[s_])) for r in range(ra, rb) for s_ in range(rp[r], rp[r + 1]))
-                assert triples == ref, (trial, b, sorted_slots)
+        _check_slices(n, rp, col, eid, row_start, True)
 
 
 def test_sweep_owner_matches_python_assignment():

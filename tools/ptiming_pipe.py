@@ -28,7 +28,9 @@ def st(x): return "mean %.0f  min-cta %.0f  max-cta %.0f" % (x.mean(), x.min(axi
 print("ncta", ncta.value)
 print("pass 1 (gathers + barrier A)        ", st(t[:, :, 1] - t[:, :, 0]))
 print("pass 2 (row sum, thread 0)          ", st(t[:, :, 2] - t[:, :, 1]))
-print("poll warps: after barrier A -> coef  ", st(t[:, :, 4] - t[:, :, 3]))
+print("update: barrier B -> un, zn computed  ", st(t[:, :, 3] - t[:, :, 6]))
+print("update: -> stores issued            ", st(t[:, :, 4] - t[:, :, 3]))
+print("update: -> warp sums done           ", st(t[:, :, 5] - t[:, :, 4]))
 print("rows done -> barrier B passed (t0)  ", st(t[:, :, 6] - t[:, :, 2]))
 print("update, stores, block sums (t0)     ", st(t[:, :, 7] - t[:, :, 6]))
 print("end -> next start (barrier C)       ", st(t[1:, :, 0] - t[:-1, :, 7]))
