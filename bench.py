@@ -328,6 +328,8 @@ def run_ours(args, rank, local_rank, world):
                   "writes its own Lanczos basis (> L2)",
             "timing": "sum of per-iteration CUDA-event brackets on the library stream, max over ranks",
             "lanczos_steps_per_solve": counters["lanczos_steps"] / max(counters["fiedler_solves"], 1),
+            "lanczos_us_per_step": lz_us, "lanczos_ms_per_iter": lz["ms"] / K,
+            "other_kernels_ms_per_iter": dev_s * 1e3 / K - lz["ms"] / K,
             "nnz_union": sizes["nnz_union"], "nnz_active_final": sizes["nnz_active"],
             "wall_s_timed_region_incl_flush": wall_timed, "final_lambda2": float(info["f_hist"][-1]), "dual_bound": u,
             "spmv_us_l2_resident": spmv_ms * 1e3, "spmv_us_l2_flushed": spmv_cold_ms * 1e3,

@@ -869,7 +869,7 @@ void finalize_ritz(macb_ctx* c, int k, const std::vector<double>& s, FiedlerResu
     std::vector<double> coef(k);
     for (int t = 0; t < k; ++t) coef[t] = s[t] / c->h_beta[t];
     CK(cudaMemcpyAsync(c->d_coef, coef.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
-    k_ritz<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(),
+    k_ritz<<<c->grid_for((int64_t)c->n * 2), kBlock, 0, c->stream>>>(c->n, c->ld, k, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(),
                                                         c->persist_v == 5 ? c->d_jrow : nullptr, nullptr);
     k_center_normalize<<<c->grid_for(c->n), kBlock, 0, c->stream>>>(c->n, c->d_v, c->d_sc);
     launch_spmv<2>(c, c->d_v, c->d_y);
@@ -1110,7 +1110,7 @@ void enqueue_fiedler_device(macb_ctx* c, double tol, int max_steps, bool use_war
     c->rr_launch = R;
     launch_persist(c, k_lim + 1, true);
     c->rr_launch.enabled = 0;
-    k_ritz<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->ld, 0, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(), small ? nullptr : c->d_jrow,
+    k_ritz<<<c->grid_for((int64_t)n * 2), kBlock, 0, c->stream>>>(n, c->ld, 0, c->d_basis, c->d_coef, c->d_v, c->d_sc, c->ws(), small ? nullptr : c->d_jrow,
                                                         c->d_rr_out);
     k_center_normalize<<<c->grid_for(n), kBlock, 0, c->stream>>>(n, c->d_v, c->d_sc);
     launch_spmv<2>(c, c->d_v, c->d_y);

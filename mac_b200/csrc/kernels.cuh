@@ -2182,22 +2182,53 @@ __global__ void __launch_bounds__(kBlock) k_ritz(int n, int ld, int k, const dou
                                                  const int* __restrict__ perm /* engine -> caller numbering, or null */,
                                                  const RrOut* __restrict__ rr /* k decided on the device, or null */) {
     __shared__ double sm[2 * kWarpsPerBlock];
+    __shared__ double part[kWarpsPerBlock][128 + 4];
     __shared__ int flag;
     if (rr) k = rr->k;
+    // A tile of 128 nodes per block, four consecutive nodes per lane (32-byte loads: every warp reads 1 KB runs of a basis
+    // vector -- 256-byte runs left HBM at 2.8 TB/s, ncu), the basis vectors dealt out to the block's warps (warp g takes
+    // t = k-1-g, k-1-g-W, ...).  ld is a multiple of 32, so the loads are aligned and stay inside the row.
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    constexpr int W = kWarpsPerBlock;
     double r0 = 0.0, r1 = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        // newest vectors first: the last ~100 MB the Lanczos kernel wrote are still in L2
-        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        int t = k;
-        for (; t >= 8; t -= 8) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = fma(coef[t - 1 - q], basis[(size_t)(t - 1 - q) * ld + i], acc[q]);
+    const int ntiles = (n + 127) >> 7;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i4 = tile * 128 + 4 * lane;
+        double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+        if (i4 < ld) {
+            // newest vectors first: the last ~100 MB the Lanczos kernel wrote are still in L2
+            int t = k - 1 - grp;
+            for (; t >= W; t -= 2 * W) {
+                const double2* p0 = reinterpret_cast<const double2*>(basis + (size_t)t * ld + i4);
+                const double2* p1 = reinterpret_cast<const double2*>(basis + (size_t)(t - W) * ld + i4);
+                const double2 a0 = __ldg(p0), a1 = __ldg(p0 + 1), b0 = __ldg(p1), b1 = __ldg(p1 + 1);
+                const double c0 = coef[t], c1 = coef[t - W];
+                acc[0][0] = fma(c0, a0.x, acc[0][0]); acc[0][1] = fma(c0, a0.y, acc[0][1]);
+                acc[0][2] = fma(c0, a1.x, acc[0][2]); acc[0][3] = fma(c0, a1.y, acc[0][3]);
+                acc[1][0] = fma(c1, b0.x, acc[1][0]); acc[1][1] = fma(c1, b0.y, acc[1][1]);
+                acc[1][2] = fma(c1, b1.x, acc[1][2]); acc[1][3] = fma(c1, b1.y, acc[1][3]);
+            }
+            if (t >= 0) {
+                const double2* p0 = reinterpret_cast<const double2*>(basis + (size_t)t * ld + i4);
+                const double2 a0 = __ldg(p0), a1 = __ldg(p0 + 1);
+                const double c0 = coef[t];
+                acc[0][0] = fma(c0, a0.x, acc[0][0]); acc[0][1] = fma(c0, a0.y, acc[0][1]);
+                acc[0][2] = fma(c0, a1.x, acc[0][2]); acc[0][3] = fma(c0, a1.y, acc[0][3]);
+            }
         }
-        for (; t > 0; --t) acc[0] = fma(coef[t - 1], basis[(size_t)(t - 1) * ld + i], acc[0]);
-        double yv = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-        out[perm ? perm[i] : i] = yv;
-        r0 += yv;
-        r1 = fma(yv, yv, r1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part[grp][4 * lane + q] = acc[0][q] + acc[1][q];
+        __syncthreads();
+        const int i = tile * 128 + (int)threadIdx.x;
+        if (threadIdx.x < 128 && i < n) {
+            double yv = 0.0;
+#pragma unroll
+            for (int g = 0; g < W; ++g) yv += part[g][threadIdx.x];
+            out[perm ? perm[i] : i] = yv;
+            r0 += yv;
+            r1 = fma(yv, yv, r1);
+        }
+        __syncthreads();
     }
     double v[2] = {r0, r1};
     if (grid_reduce<2>(v, ws, sm, &flag)) {
@@ -2353,10 +2384,17 @@ __global__ void __launch_bounds__(kSel2Block, 1) k_sel2_hist(int64_t m, const do
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * kSel2Block;
     const int64_t mceil = ((m + 31) / 32) * 32;
-    for (int64_t e = (int64_t)blockIdx.x * kSel2Block + threadIdx.x; e < mceil; e += stride) {
-        const bool ok = e < m;
-        const unsigned int d = ok ? (unsigned int)(order_key(g[e]) >> 49) : 0u;
-        sel2_hist_add(sh2, d, ok);
+    // eight loads in flight per thread: one load per trip of a loop with a warp-synchronous step in it is a chain of L2 latencies
+    for (int64_t e0 = (int64_t)blockIdx.x * kSel2Block + threadIdx.x; e0 < mceil; e0 += 8 * stride) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (e0 + q * stride < m) ? ld_stream(g + e0 + q * stride) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (e0 + q * stride >= mceil) break;   // warp-uniform
+            const bool ok = e0 + q * stride < m;
+            sel2_hist_add(sh2, ok ? (unsigned int)(order_key(v[q]) >> 49) : 0u, ok);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) {
@@ -2369,9 +2407,15 @@ __global__ void __launch_bounds__(kSel2Block, 1) k_sel2_hist(int64_t m, const do
     __syncthreads();
     if (!last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < kSel2Bins; i += kSel2Block) {
-        sh2[i] = __ldcg(ghist + i);
-        ghist[i] = 0u;   // ready for the next selection
+    {   // all 32 loads of the thread first, then the stores: interleaved they serialise on the L2 latency (17 of 27 us, ncu)
+        unsigned int hv[kSel2Bins / kSel2Block];
+#pragma unroll
+        for (int q = 0; q < kSel2Bins / kSel2Block; ++q) hv[q] = __ldcg(ghist + threadIdx.x + q * kSel2Block);
+#pragma unroll
+        for (int q = 0; q < kSel2Bins / kSel2Block; ++q) {
+            sh2[threadIdx.x + q * kSel2Block] = hv[q];
+            if (hv[q]) ghist[threadIdx.x + q * kSel2Block] = 0u;   // ready for the next selection
+        }
     }
     __syncthreads();
     sel2_find_from_top(sh2, kSel2Bins, k, warp_tot, &digit, &above_s, &count_s);
@@ -2390,19 +2434,22 @@ __global__ void __launch_bounds__(kBlock) k_sel2_compact(int64_t m, const double
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t mceil = ((m + 31) / 32) * 32;
     const int lane = threadIdx.x & 31;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mceil; e += stride) {
-        unsigned long long key = 0ull;
-        bool hit = false;
-        if (e < m) {
-            key = order_key(g[e]);
-            hit = (unsigned int)(key >> 49) == bin;
-        }
-        const unsigned int bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-            unsigned int base = 0;
-            if (lane == __ffs(bal) - 1) base = atomicAdd(&s2->ncand, (unsigned int)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-            if (hit) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < mceil; e0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (e0 + q * stride < m) ? ld_stream(g + e0 + q * stride) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (e0 + q * stride >= mceil) break;   // warp-uniform
+            const unsigned long long key = order_key(v[q]);
+            const bool hit = (e0 + q * stride < m) && (unsigned int)(key >> 49) == bin;
+            const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+                unsigned int base = 0;
+                if (lane == __ffs(bal) - 1) base = atomicAdd(&s2->ncand, (unsigned int)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                if (hit) cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+            }
         }
     }
 }
@@ -2422,15 +2469,22 @@ __device__ __forceinline__ void sel2_refine_body(int64_t n, const unsigned long 
         for (int i = threadIdx.x; i < 8192; i += kSel2Block) hist[i] = 0u;
         __syncthreads();
         const int64_t nceil = ((n + 31) / 32) * 32;
-        for (int64_t i = threadIdx.x; i < nceil; i += kSel2Block) {
-            bool ok = false;
-            unsigned int d = 0;
-            if (i < n) {
-                const unsigned long long key = FROM_G ? order_key(g[i]) : cand[i];
-                ok = (key & decided) == prefix;
-                d = (unsigned int)((key >> shifts[p]) & (unsigned long long)(nb - 1));
+        for (int64_t i0 = threadIdx.x; i0 < nceil; i0 += 8 * kSel2Block) {
+            unsigned long long kq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t i = i0 + q * kSel2Block;
+                kq[q] = (i < n) ? (FROM_G ? order_key(g[i]) : __ldcg(cand + i)) : 0ull;
             }
-            sel2_hist_add(hist, d, ok);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t i = i0 + q * kSel2Block;
+                if (i >= nceil) break;   // warp-uniform
+                const bool ok = (i < n) && (kq[q] & decided) == prefix;
+                // plain shared-memory atomics: mantissa digits are all different inside a warp, where the match-any aggregation of
+                // sel2_hist_add degenerates into 32 rounds per call (it made this kernel 34 us for 50 000 candidates)
+                if (ok) atomicAdd(&hist[(unsigned int)((kq[q] >> shifts[p]) & (unsigned long long)(nb - 1))], 1u);
+            }
         }
         __syncthreads();
         sel2_find_from_top(hist, 8192, rem, warp_tot, digit, above_s, count_s);   // bins >= nb are empty

@@ -8,7 +8,7 @@ from mac_b200 import synth, _lib
 from mac_b200.solvers import MAC
 which = sys.argv[1] if len(sys.argv) > 1 else "dense"
 if which in ("H", "dense"):
-    fixed, cand, n, k, x0 = synth.headline()
+    fixed, cand, n, k, x0 = synth.headline(m=int(os.environ.get("MACB_PT_M", 1000000)))
     if which == "dense":
         x0 = np.full(len(x0), 0.2)
 else:

@@ -1,5 +1,4 @@
-MACB_LIB=mac_b200/libmacb200_timing.so timeout 120 python tools/ptiming_pipe.py H 2>&1 | tail -11
-MACB_LIB=mac_b200/libmacb200_timing.so timeout 120 python tools/ptiming_pipe.py dense 2>&1 | tail -11
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+MACB_LIB=mac_b200/libmacb200_timing.so timeout 120 python tools/ptiming_pipe.py dense 2>&1 | tail -10
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --steps 20 --warmup 3 --no-ksweep --no-hbm-spmv 2>&1 | tail -1 | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
