@@ -2494,6 +2494,45 @@ __device__ __forceinline__ void sel2_refine_body(int64_t n, const unsigned long 
         rem -= *above_s;
         eq = *count_s;
         __syncthreads();
+        if (p < 3 && eq <= (unsigned int)kSel2Block) {
+            // A handful of candidates left (typically after the first pass): rank them directly instead of three more histogram
+            // passes whose cost is all fixed overhead.  One key per thread; every thread counts the keys above and equal to its own.
+            unsigned long long* list = reinterpret_cast<unsigned long long*>(hist);   // [kSel2Block]
+            unsigned int* cnt = hist + 2 * kSel2Block;
+            if (threadIdx.x == 0) *cnt = 0u;
+            __syncthreads();
+            for (int64_t i0 = threadIdx.x; i0 < n; i0 += 8 * kSel2Block) {
+                unsigned long long kq[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int64_t i = i0 + q * kSel2Block;
+                    kq[q] = (i < n) ? (FROM_G ? order_key(g[i]) : __ldcg(cand + i)) : 0ull;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (i0 + q * kSel2Block < n && (kq[q] & decided) == prefix) list[atomicAdd(cnt, 1u)] = kq[q];
+            }
+            __syncthreads();
+            const unsigned int c = *cnt;   // == eq
+            if (threadIdx.x < c) {
+                const unsigned long long mine = list[threadIdx.x];
+                unsigned int gt = 0, same = 0;
+                for (unsigned int j = 0; j < c; ++j) {
+                    const unsigned long long o = list[j];
+                    gt += (o > mine) ? 1u : 0u;
+                    same += (o == mine) ? 1u : 0u;
+                }
+                // exactly the threads holding the k-th largest key satisfy this; they all write the same values
+                if ((long long)gt < rem && rem <= (long long)(gt + same)) {
+                    st->prefix = mine;
+                    st->mask = ~0ull;
+                    st->remaining = rem - (long long)gt;
+                    st->count_gt = cgt + (long long)gt;
+                    st->eq_total = (long long)same;
+                }
+            }
+            return;
+        }
     }
     if (threadIdx.x == 0) {
         st->prefix = prefix;
