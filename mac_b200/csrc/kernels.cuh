@@ -1834,7 +1834,8 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
         // ---- pass 1: products of the CTA's slots with the gathered z_phase
         lz_gather_products_tagged<VB>(Z, scol, jval, ns, tid, tag, prod, &sh.give_up);
         // The loads of the tail (the row's state / the polling lane's record) are issued before the barrier that ends pass 1.
-        // (Issued one batch of gathers earlier they change nothing -- measured: the tail is bound by issue slots, not by them.)
+        // (Issued one batch of gathers earlier they change nothing -- measured: the tail is bound by the shared-memory / shuffle
+        // pipe the row sums keep full, not by these loads.  See DESIGN.md, section 5.)
         double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, r4 = 0.0;
         const bool polling = warp >= first_poll_warp;
         const unsigned int pb = (unsigned int)(tid - first_poll_warp * 32);
