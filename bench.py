@@ -346,7 +346,7 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": f"{h.lanczos_kernel_name()}: one launch per eigen-solve (solver CTAs + one Rayleigh-Ritz "
                      "CTA); per Lanczos step one SpMV (8-byte gathers of the published vector, slots in column order), row sums along "
-                     "jagged diagonals and a pipelined three-term update whose reduction overlaps the next SpMV",
+                     "32-row slices and a pipelined three-term update whose reduction overlaps the next SpMV",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "us_per_lanczos_step": lz_us, "lanczos_steps_timed": lz["phases"],
                      "share_of_timed_region": lz["ms"] / (dev_max * 1e3),

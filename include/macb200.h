@@ -94,6 +94,11 @@ int macb_topk(macb_handle h, int64_t k, double* s);
 /* Same LP oracle for an arbitrary host vector g[m] (no handle state involved). */
 int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s);
 
+/* macb_topk_dense / macb_round_nearest_dense keep one internal handle per (device, m) (at most four, least recently used first
+ * out), so that a caller-side Frank-Wolfe loop (frankwolfe.py:60 calls solve_lp every iteration) does not pay a handle per call.
+ * This releases them. */
+void macb_dense_cache_clear(void);
+
 /* Replaces round_nearest(w, k, weights=kappa, break_ties_decimal_tol=decimals) (rounding.py:30-42, called at
  * mac.py:207): the k largest entries in the lexicographic order (numpy.round(w, decimals), kappa); entries equal in
  * both keys are taken lowest index first (numpy's argpartition leaves that order unspecified).  w[m] in,

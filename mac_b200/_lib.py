@@ -62,6 +62,8 @@ def lib():
     _sig(L.macb_evaluate_batch, [H, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp])
     _sig(L.macb_topk, [H, C.c_int64, _dp])
     _sig(L.macb_topk_dense, [C.c_int, _dp, C.c_int64, C.c_int64, _dp])
+    L.macb_dense_cache_clear.argtypes = []
+    L.macb_dense_cache_clear.restype = None
     _sig(L.macb_round_nearest, [H, _dp, C.c_int64, C.c_int, _dp])
     _sig(L.macb_round_nearest_dense, [C.c_int, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp])
     _sig(L.macb_fw_run, [H, C.c_int64, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -361,6 +363,11 @@ class Handle:
 
     def device_sync(self):
         self._check(self._L.macb_device_sync(self._h), "macb_device_sync")
+
+
+def dense_cache_clear():
+    """Release the handles `topk_dense` / `round_nearest_dense` keep per (device, m)."""
+    lib().macb_dense_cache_clear()
 
 
 def topk_dense(g, k, device=-1):

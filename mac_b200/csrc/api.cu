@@ -1724,19 +1724,68 @@ int macb_round_nearest(macb_handle h, const double* w, int64_t k, int decimals, 
     });
 }
 
+namespace {
+// Handles of the array-only entry points (no graph: the LP oracle and the rounding need only per-candidate arrays), kept per
+// (device, m) so that a user-supplied Frank-Wolfe loop calling solve_subset_box_lp every iteration does not pay a handle
+// (allocations, stream, pinned buffers: ~10 ms at m = 1M) per call.  At most kDenseCache entries, least recently used first out.
+constexpr size_t kDenseCache = 4;
+struct DenseEntry {
+    int device;
+    int64_t m;
+    macb_handle h;
+    uint64_t stamp;
+};
+std::mutex g_dense_mutex;
+std::vector<DenseEntry> g_dense;
+uint64_t g_dense_clock = 0;
+
+// g_dense_mutex held by the caller
+macb_handle dense_handle(int device, int64_t m, int* rc) {
+    for (DenseEntry& e : g_dense)
+        if (e.device == device && e.m == m) {
+            e.stamp = ++g_dense_clock;
+            *rc = MACB_OK;
+            return e.h;
+        }
+    std::vector<int32_t> zi((size_t)m, 0);
+    std::vector<double> zk((size_t)m, 0.0);
+    macb_handle h = nullptr;
+    *rc = macb_create(1, 0, nullptr, nullptr, nullptr, m, zi.data(), zi.data(), zk.data(), device, &h);
+    if (*rc != MACB_OK) return nullptr;
+    if (g_dense.size() >= kDenseCache) {
+        size_t old = 0;
+        for (size_t q = 1; q < g_dense.size(); ++q)
+            if (g_dense[q].stamp < g_dense[old].stamp) old = q;
+        macb_destroy(g_dense[old].h);
+        g_dense.erase(g_dense.begin() + (long)old);
+    }
+    g_dense.push_back(DenseEntry{device, m, h, ++g_dense_clock});
+    return h;
+}
+}  // namespace
+
+void macb_dense_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_dense_mutex);
+    for (DenseEntry& e : g_dense) macb_destroy(e.h);
+    g_dense.clear();
+}
+
 int macb_round_nearest_dense(int device, const double* w, const double* weights, int64_t m, int64_t k, int decimals,
                              double* rounded) {
     if (!w || !weights || !rounded || m < 1 || k < 0 || k > m) {
         g_create_error = "macb_round_nearest_dense: bad arguments";
         return MACB_ERR_ARG;
     }
-    std::vector<int32_t> zi((size_t)m, 0);
-    macb_handle h = nullptr;
-    int rc = macb_create(1, 0, nullptr, nullptr, nullptr, m, zi.data(), zi.data(), weights, device, &h);
-    if (rc != MACB_OK) return rc;
-    rc = macb_round_nearest(h, w, k, decimals, rounded);
+    std::lock_guard<std::mutex> lk(g_dense_mutex);
+    int rc = MACB_OK;
+    macb_handle h = dense_handle(device, m, &rc);
+    if (!h) return rc;
+    rc = guarded(h, [&]() {   // this call's weights in place of the handle's
+        CK(cudaMemcpyAsync(h->d_kappa, weights, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+        return (int)MACB_OK;
+    });
+    if (rc == MACB_OK) rc = macb_round_nearest(h, w, k, decimals, rounded);
     if (rc != MACB_OK) g_create_error = h->err;
-    macb_destroy(h);
     return rc;
 }
 
@@ -1745,12 +1794,10 @@ int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s
         g_create_error = "macb_topk_dense: bad arguments";
         return MACB_ERR_ARG;
     }
-    // A throw-away handle over an edgeless 1-node... the LP oracle needs only the candidate arrays.
-    std::vector<int32_t> zi((size_t)m, 0);
-    std::vector<double> zk((size_t)m, 0.0);
-    macb_handle h = nullptr;
-    int rc = macb_create(1, 0, nullptr, nullptr, nullptr, m, zi.data(), zi.data(), zk.data(), device, &h);
-    if (rc != MACB_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_dense_mutex);
+    int rc = MACB_OK;
+    macb_handle h = dense_handle(device, m, &rc);
+    if (!h) return rc;
     rc = guarded(h, [&]() {
         CK(cudaMemcpyAsync(h->d_g, g, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
         launch_topk(h, h->d_g, h->d_x, k, h->d_sel);
@@ -1760,7 +1807,6 @@ int macb_topk_dense(int device, const double* g, int64_t m, int64_t k, double* s
         return (int)MACB_OK;
     });
     if (rc != MACB_OK) g_create_error = h->err;
-    macb_destroy(h);
     return rc;
 }
 

@@ -264,6 +264,35 @@ def test_topk_bit_exact_and_tie_rules():
     assert np.allclose(x, [0.5, 0.5], atol=0.01)
 
 
+def test_dense_entry_points_reuse_their_handle():
+    """solve_subset_box_lp / round_nearest on host arrays keep one handle per (device, m): repeated calls with new values
+    and new weights must not see anything of the previous call, and are much cheaper than the first."""
+    import time
+    from mac_b200 import _lib
+    _lib.dense_cache_clear()
+    rng = np.random.default_rng(17)
+    m, k = 200_000, 40_000
+    times = []
+    for trial in range(4):
+        g = rng.random(m) ** 2
+        t0 = time.perf_counter()
+        s = solve_subset_box_lp(g, k)
+        times.append(time.perf_counter() - t0)
+        ref = np.zeros(m)
+        ref[np.argsort(-g, kind="stable")[:k]] = 1.0
+        assert np.array_equal(s, ref)
+    assert min(times[1:]) < times[0]
+    w = np.round(rng.random(m), 2)          # many exact ties at the k-th value
+    for trial in range(3):
+        weights = rng.random(m)             # new tie-break weights every call
+        r = _lib.round_nearest_dense(w, weights, k, 10)
+        assert r.sum() == k and np.array_equal(r, orc.round_nearest(w, k, weights=weights, break_ties_decimal_tol=10))
+    for mm in (10, 1000, 5000, 70000, 10):   # more sizes than cache entries
+        g = rng.random(mm)
+        assert solve_subset_box_lp(g, mm // 2).sum() == mm // 2
+    _lib.dense_cache_clear()
+
+
 def test_round_nearest_tiebreak_matches_reference_semantics():
     """rounding.py:30-42 on the device: lexicographic (round(w, 10), weight) top-k."""
     rng = np.random.default_rng(0)
