@@ -179,17 +179,22 @@ def ksweep(world, rank, local_rank):
         n, m = int(z["n"]), len(cand[0])
         budgets = [int(p * m) for p in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)]
         naive = NaiveGreedy(cand[2])
-        farm.sweep_budgets(fixed, cand, n, budgets, naive.subset, device=local_rank, max_iters=1)   # warm-up: contexts, engines
-        sync_max(0.0)
-        t0 = time.perf_counter()
-        res = farm.sweep_budgets(fixed, cand, n, budgets, naive.subset, device=local_rank, max_iters=20)
-        dt = sync_max(time.perf_counter() - t0)
+        streams = os.environ.get("MACB_KSWEEP_STREAMS", "auto")   # budgets of a rank solved concurrently on its GPU
+        streams = streams if streams == "auto" else int(streams)
+        # the graph resident on the GPU before the loop over budgets, as in g2o_experiment.py:284 (one MAC per dataset)
+        with farm.SweepPool(fixed, cand, n, device=local_rank, streams=streams) as pool:
+            pool.sweep(budgets, naive.subset, max_iters=1)   # warm-up: contexts, engines
+            sync_max(0.0)
+            t0 = time.perf_counter()
+            res = pool.sweep(budgets, naive.subset, max_iters=20)
+            dt = sync_max(time.perf_counter() - t0)
+            streams = pool.streams
         runs = gold[name]["runs"]
         dlam = [abs(lam - runs[str(k)]["unrounded_l2"]) / runs[str(k)]["unrounded_l2"] for (k, r, w, u, lam) in res]
         du = [abs(u - runs[str(k)]["u"]) / runs[str(k)]["u"] for (k, r, w, u, lam) in res]
         out[name] = {"seconds": dt, "budgets": len(budgets), "max_rel_dlambda2_vs_reference": max(dlam),
                      "median_rel_dlambda2_vs_reference": float(np.median(dlam)), "max_rel_du_vs_reference": max(du),
-                     "selected_ok": all(int(r.sum()) == k for (k, r, w, u, lam) in res)}
+                     "selected_ok": all(int(r.sum()) == k for (k, r, w, u, lam) in res), "streams_per_gpu": streams}
     out["note"] = ("deviations above ~1e-6 come from budgets whose Frank-Wolfe trajectory crosses an LP tie (city10000: all kappa = 100; "
                    "tests/test_gpu_parity.py asserts the fork happens inside the tie window)")
     return out

@@ -175,6 +175,11 @@ int macb_spmv_engine(macb_handle h, int engine);
  * (CUDA-graph engine); "" before the first solve.  The pointer stays valid for the life of the handle. */
 const char* macb_lanczos_kernel_name(macb_handle h);
 
+/* CTAs (= SMs: 1024 threads and most of the shared memory each) one eigen-solve launch of this handle occupies, and the SMs of its
+ * device: how many independent solves (budgets of a K-sweep, g2o_experiment.py:306) fit on the GPU side by side.  Builds the engine
+ * (layout, buffers) if no solve has done so yet. */
+int macb_lanczos_footprint(macb_handle h, int32_t* ctas, int32_t* sm_count);
+
 /* Measured L2 -> SM read bandwidth of `device` (-1: current): every SM streams a `bytes`-sized, L2-resident buffer
  * `reps` times with 16-byte loads that bypass L1.  The Lanczos kernels' matrix is L2-resident at the BASELINE sizes, so
  * this -- not the HBM copy bandwidth -- is the roofline that binds them (bench.py `roofline.l2`).  Measurement only;

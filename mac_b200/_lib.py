@@ -79,6 +79,7 @@ def lib():
     _sig(L.macb_device_sync, [H])
     _sig(L.macb_lanczos_kernel_time, [H, _dp, _lp, _dp])
     _sig(L.macb_lanczos_kernel_name, [H], C.c_char_p)
+    _sig(L.macb_lanczos_footprint, [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)])
     _sig(L.macb_spmv_engine, [H, C.c_int])
     _sig(L.macb_tridiag_smallest, [_dp, _dp, C.c_int, _dp, _dp])
     _sig(L.macb_host_build_pattern, [C.c_int32, C.c_int64, _ip, _ip, C.c_int64, _ip, _ip, _ip, _ip, _ip, _lp])
@@ -360,6 +361,12 @@ class Handle:
 
     def lanczos_kernel_name(self):
         return self._L.macb_lanczos_kernel_name(self._h).decode()
+
+    def lanczos_footprint(self):
+        """(CTAs one eigen-solve launch occupies, SMs of the device).  Builds the engine if no solve has done so yet."""
+        a, b = C.c_int32(), C.c_int32()
+        self._check(self._L.macb_lanczos_footprint(self._h, C.byref(a), C.byref(b)), "macb_lanczos_footprint")
+        return a.value, b.value
 
     def device_sync(self):
         self._check(self._L.macb_device_sync(self._h), "macb_device_sync")

@@ -2171,6 +2171,16 @@ const char* macb_lanczos_kernel_name(macb_handle h) {
     }
 }
 
+int macb_lanczos_footprint(macb_handle h, int32_t* ctas, int32_t* sm_count) {
+    if (!h || !ctas || !sm_count) return MACB_ERR_ARG;
+    return guarded(h, [&]() {
+        ensure_basis(h, 0);   // builds the engine (layout, buffers) if no solve has done so yet
+        *ctas = h->p_ncta > 0 ? h->p_ncta + (h->dev_rr ? 1 : 0) : 0;
+        *sm_count = h->sm_count;
+        return (int)MACB_OK;
+    });
+}
+
 int macb_measure_l2_bandwidth(int device, int64_t bytes, int reps, double* gbs) {
     if (bytes < (1 << 20) || reps < 1 || !gbs) return MACB_ERR_ARG;
     try {

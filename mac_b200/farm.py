@@ -111,72 +111,135 @@ def farm_comm(device=None):
     return _COMM
 
 
-def sweep_budgets(fixed, cand, n, budgets, x_init_fn, device=None, max_iters=20, streams=1, comm="env", **solve_kw):
-    """The g2o protocol (g2o_experiment.py:306-321) farmed over ranks: for each budget K,
-    x_init = x_init_fn(K), MAC.solve(K, x_init, max_iters=20, rounding='nearest').
-    Returns [(K, rounded, w, u, lambda2_unrounded)] in budget order on every rank.
+class SweepPool:
+    """The graph of one budget sweep resident on this rank's GPU, `streams` times: one MAC handle (own CUDA stream, own host
+    thread while a sweep runs) per budget solved concurrently.  A pose graph (n <= 1e4) occupies 6-21 of the 148 SMs, so
+    independent budgets overlap almost perfectly; `streams="auto"` asks the engine how many of its launches fit side by side
+    (`macb_lanczos_footprint`).  The counterpart of the one `MAC(...)` the reference builds per dataset before its budget loop
+    (g2o_experiment.py:284); reuse it for several sweeps of the same graph, `close()` it when done."""
 
-    One process per GPU (torchrun or any launcher that sets RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT); the budgets are
-    assigned longest-first (`macb_sweep_owner`), every rank solves its share through `macb_sweep`, and ONE ncclAllGather of
-    fixed-size records (C-ABI, `macb_comm_allgather`) leaves all results on every rank -- no torch, no pickling.
+    def __init__(self, fixed, cand, n, device=None, streams="auto"):
+        from .solvers.mac import MAC
+        _, local_rank, _ = dist_env()
+        self.dev = local_rank if device is None else device
+        self.fixed, self.cand, self.n, self.m = fixed, cand, n, len(cand[0])
+        self.macs = [MAC(fixed, cand, n, device=self.dev)]
+        if streams == "auto":
+            ctas, sms = self.macs[0]._h.lanczos_footprint()
+            streams = max(1, min(sms // max(ctas, 1), 8))
+        self.streams = max(1, int(streams))
 
-    `streams` > 1 (single process only) runs that many budgets concurrently on one GPU, each on its own handle / CUDA stream /
-    host thread: a pose graph (n <= 1e4) occupies 1-20 of the 148 SMs, so independent budgets overlap almost perfectly.
-    Results do not depend on `streams` or on the number of ranks (every solve is a pure function of its input)."""
-    import numpy as np
-    from .solvers.mac import MAC
-    rank, local_rank, world = dist_env()
-    dev = local_rank if device is None else device
-    m = len(cand[0])
-    budgets = [int(k) for k in budgets]
-    if comm == "env":
-        comm = farm_comm(dev)
-    if comm is not None or streams <= 1:
-        mac = MAC(fixed, cand, n, device=dev)
-        try:
+    def _mac(self, slot):
+        """Handle of worker `slot` (created by the worker itself on first use: the host-side layout builds run in parallel)."""
+        from .solvers.mac import MAC
+        while len(self.macs) <= slot:
+            self.macs.append(None)
+        if self.macs[slot] is None:
+            self.macs[slot] = MAC(self.fixed, self.cand, self.n, device=self.dev)
+        return self.macs[slot]
+
+    def sweep(self, budgets, x_init_fn, max_iters=20, comm="env", **solve_kw):
+        """[(K, rounded, w, u, lambda2_unrounded)] in budget order, identical on every rank."""
+        import queue
+        import threading
+        import numpy as np
+        from . import _lib
+        m = self.m
+        budgets = [int(k) for k in budgets]
+        if comm == "env":
+            comm = farm_comm(self.dev)
+        if self.streams <= 1:
+            mac = self.macs[0]
             x_inits = np.stack([np.asarray(x_init_fn(k), dtype=float) for k in budgets]) if budgets else np.zeros((0, m))
             rounded, w, u, lam, iters = mac._h.sweep(comm, budgets, x_inits, max_iters=max_iters,
                                                      rel_gap_tol=solve_kw.get("relative_duality_gap_tol", 1e-4),
                                                      grad_norm_tol=solve_kw.get("grad_norm_tol", 1e-8),
                                                      min_sel_tol=mac.min_selection_weight_tol, fiedler_max_steps=mac.fiedler_max_steps)
             return [(k, rounded[i], w[i], float(u[i]), float(lam[i])) for i, k in enumerate(budgets)]
-        finally:
-            mac.close()
 
-    import queue
-    import threading
-    costs = [1.0 + (m - k) / max(m, 1) for k in budgets]
+        nranks = comm.nranks if comm is not None else 1
+        myrank = comm.rank if comm is not None else 0
+        owner = _lib.sweep_owner(budgets, m, nranks) if budgets else np.zeros(0, dtype=np.int32)
+        mine = [i for i in range(len(budgets)) if owner[i] == myrank]
+        costs = [1.0 + (m - k) / max(m, 1) for k in budgets]
+        todo = queue.Queue()
+        for i in sorted(mine, key=lambda i: -costs[i]):
+            todo.put(i)
+        local, errors = {}, []
 
-    def solve_with(mac, k):
-        rounded, w, u = mac.solve(k, x_init_fn(k), max_iters=max_iters, **solve_kw)
-        return (k, rounded.astype("u1"), w, u, mac.evaluate_objective(w))
+        def worker(slot):
+            try:
+                mac = self._mac(slot)
+                while True:
+                    try:
+                        i = todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    k = budgets[i]
+                    rounded, w, u = mac.solve(k, x_init_fn(k), max_iters=max_iters, **solve_kw)
+                    local[i] = (k, rounded.astype("u1"), w, u, mac.evaluate_objective(w))
+            except Exception as e:  # surfaced below
+                errors.append(e)
 
-    todo = queue.Queue()
-    for i in sorted(range(len(budgets)), key=lambda i: -costs[i]):
-        todo.put(i)
-    local, errors = {}, []
+        nthreads = min(self.streams, max(len(mine), 1))
+        while len(self.macs) < nthreads:
+            self.macs.append(None)
+        threads = [threading.Thread(target=worker, args=(slot,)) for slot in range(nthreads)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        if comm is None:
+            return [local[i] for i in range(len(budgets))]
+        # one fixed-size record per budget: rounded mask, relaxed solution, dual bound, lambda2; every rank sends the same count
+        per_rank = [[i for i in range(len(budgets)) if owner[i] == r] for r in range(nranks)]
+        slots = max(1, max(len(p) for p in per_rank))
+        buf = np.zeros((slots, 2 * m + 2))
+        for j, i in enumerate(mine):
+            k, rounded, w, u, lam = local[i]
+            buf[j, :m] = rounded
+            buf[j, m:2 * m] = w
+            buf[j, 2 * m] = u
+            buf[j, 2 * m + 1] = lam
+        allb = comm.allgather(buf)
+        out = [None] * len(budgets)
+        for r in range(nranks):
+            for j, i in enumerate(per_rank[r]):
+                rec = allb[r, j]
+                out[i] = (budgets[i], rec[:m].astype("u1"), rec[m:2 * m].copy(), float(rec[2 * m]), float(rec[2 * m + 1]))
+        return out
 
-    def worker():
-        mac = None
-        try:
-            mac = MAC(fixed, cand, n, device=dev)
-            while True:
-                try:
-                    i = todo.get_nowait()
-                except queue.Empty:
-                    return
-                local[i] = solve_with(mac, budgets[i])
-        except Exception as e:  # surfaced below
-            errors.append(e)
-        finally:
+    def close(self):
+        for mac in self.macs:
             if mac is not None:
                 mac.close()
+        self.macs = []
 
-    threads = [threading.Thread(target=worker) for _ in range(min(streams, max(len(budgets), 1)))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
-    return [local[i] for i in range(len(budgets))]
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def sweep_budgets(fixed, cand, n, budgets, x_init_fn, device=None, max_iters=20, streams=1, comm="env", pool=None, **solve_kw):
+    """The g2o protocol (g2o_experiment.py:306-321) farmed over ranks: for each budget K,
+    x_init = x_init_fn(K), MAC.solve(K, x_init, max_iters=20, rounding='nearest').
+    Returns [(K, rounded, w, u, lambda2_unrounded)] in budget order on every rank.
+
+    One process per GPU (torchrun or any launcher that sets RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT); the budgets are
+    assigned longest-first (`macb_sweep_owner`), every rank solves its share, and ONE ncclAllGather of fixed-size records
+    (C-ABI, `macb_comm_allgather`) leaves all results on every rank -- no torch, no pickling.  With `streams` <= 1 all of it
+    happens inside `macb_sweep`.
+
+    `streams` > 1 (or "auto": as many as fit) runs that many of a rank's budgets concurrently on its GPU (`SweepPool`); pass a
+    `pool` to reuse its handles across calls.  Results do not depend on `streams` or on the number of ranks (every solve is a
+    pure function of its input)."""
+    if pool is not None:
+        return pool.sweep(budgets, x_init_fn, max_iters=max_iters, comm=comm, **solve_kw)
+    with SweepPool(fixed, cand, n, device=device, streams=streams) as p:
+        return p.sweep(budgets, x_init_fn, max_iters=max_iters, comm=comm, **solve_kw)
+
+

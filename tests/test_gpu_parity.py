@@ -678,7 +678,7 @@ def test_greedy_eig_matches_oracle_restatement():
 
 
 # ------------------------------------------------------------------------------------------- farm (multi-GPU)
-def _run_farm_ranks(world):
+def _run_farm_ranks(world, streams=1):
     """`world` processes, one per GPU, each running tools/farm_check.py (macb_sweep + ncclAllGather behind the C-ABI)."""
     import socket
     import subprocess
@@ -687,7 +687,8 @@ def _run_farm_ranks(world):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     procs = []
     for r in range(world):
-        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world))
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world),
+                   MACB_FARM_STREAMS=str(streams))
         procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tools", "farm_check.py")], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
     outs = []
@@ -710,6 +711,11 @@ def test_farm_sweep_single_process_matches_solve():
         assert np.array_equal(r, r1.astype("u1")) and np.array_equal(w, w1) and u == u1
         assert abs(lam - mac.evaluate_objective(w1)) <= 1e-12 * lam
     mac.close()
+    # several budgets at a time on one GPU (own handle, stream and host thread each): same results
+    res3 = farm.sweep_budgets(fixed, cand, n, budgets, lambda k: synth.first_k_init(9000, k), max_iters=5, comm=None, streams=3)
+    for a_, b_ in zip(res, res3):
+        assert a_[0] == b_[0] and np.array_equal(a_[1], b_[1]) and np.array_equal(a_[2], b_[2]) and a_[3] == b_[3]
+        assert abs(a_[4] - b_[4]) <= 1e-12 * a_[4]
 
 
 def test_farm_sweep_two_gpus_nccl():
@@ -721,5 +727,11 @@ def test_farm_sweep_two_gpus_nccl():
     assert outs[0]["results"] == outs[1]["results"] and {o["rank"] for o in outs} == {0, 1}
     single = _run_farm_ranks(1)[0]["results"]
     for a_, b_ in zip(outs[0]["results"], single):
+        assert a_[0] == b_[0] and a_[1] == b_[1] == a_[0]
+        assert abs(a_[2] - b_[2]) <= 1e-12 * abs(b_[2]) and abs(a_[3] - b_[3]) <= 1e-12 * b_[3] and abs(a_[4] - b_[4]) <= 1e-9 * b_[4]
+    # the same with two budgets at a time per GPU (threads + one allgather of packed records)
+    outs2 = _run_farm_ranks(2, streams=2)
+    assert outs2[0]["results"] == outs2[1]["results"]
+    for a_, b_ in zip(outs2[0]["results"], single):
         assert a_[0] == b_[0] and a_[1] == b_[1] == a_[0]
         assert abs(a_[2] - b_[2]) <= 1e-12 * abs(b_[2]) and abs(a_[3] - b_[3]) <= 1e-12 * b_[3] and abs(a_[4] - b_[4]) <= 1e-9 * b_[4]
