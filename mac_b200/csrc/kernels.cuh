@@ -994,7 +994,7 @@ __device__ __forceinline__ void lz_gather_products_tagged(const double* __restri
                     __nanosleep(100);   // the producer is still in its row sums: do not fill the memory pipe with polls
                     v[q] = ld_f64_relaxed_if(U + (c[q] & kLzColMask), true, ok_zero);
                 } while (!lz_tag_ok(v[q], tag) && ++tries < (1u << 16));
-                if (!lz_tag_ok(v[q], tag)) *give_up = 1;
+                if (!lz_tag_ok(v[q], tag)) atomicExch(give_up, 1);
             }
             // inactive slots store nothing: their positions keep the zero written when the launch began
             if ((c[q] & kLzColMask) != kLzColMask) prod[(unsigned int)c[q] >> 17] = wq[q] * v[q];
@@ -1809,7 +1809,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
                    q2 = __shfl_sync(0xffffffffu, r, 16), q3 = __shfl_sync(0xffffffffu, r, 24);
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
             q0 = (q0 == q0) ? q0 : inf; q1 = (q1 == q1) ? q1 : inf; q2 = (q2 == q2) ? fabs(q2) : inf; q3 = (q3 == q3) ? q3 : inf;
-            if (*(volatile int*)&sh.give_up) q0 = inf;   // poison alpha: the Rayleigh-Ritz side sees a non-finite value and reports it
+            if (atomicOr(&sh.give_up, 0)) q0 = inf;   // poison alpha: the Rayleigh-Ritz side sees a non-finite value and reports it
             if (blockIdx.x == 0) {
                 int stop_now = 0;
                 if (lane == 0) {
@@ -1859,6 +1859,9 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
         // From here to the update the polling warps and the row warps run DIFFERENT code between the same two CTA barriers,
         // so that what a row thread keeps in registers (its state, requested from L2 before the first barrier) is not live
         // across the register-hungry polling / coefficient code: inlined into one path the allocator spills it to local memory.
+        // The two paths reach barriers 2 and 3 at different program points.  That is within PTX's rule for bar.sync (all threads
+        // of a WARP execute the same barrier instruction; the branch is warp-uniform) but compute-sanitizer's synccheck reports
+        // it; the form with one bar.sync site per barrier was built and measured: +110 bytes of spills, 6.7 -> 8.2 us per step.
         // Everything needed from L2 is requested BEFORE the barrier that ends pass 1: an L2 round trip costs ~2 500 cycles
         // while the other SMs are gathering -- as long as the row sums and the update together.
         if (polling) {
@@ -1875,7 +1878,7 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
                 const bool ok = (pb >= ncta) || lz_tag_ok(y0, tag);
                 if (__all_sync(0xffffffffu, ok)) break;
                 if (++spins > (1u << 18)) {
-                    sh.give_up = 1;
+                    atomicExch(&sh.give_up, 1);
                     break;
                 }
                 if (!ok)
