@@ -716,6 +716,14 @@ def test_farm_sweep_single_process_matches_solve():
     for a_, b_ in zip(res, res3):
         assert a_[0] == b_[0] and np.array_equal(a_[1], b_[1]) and np.array_equal(a_[2], b_[2]) and a_[3] == b_[3]
         assert abs(a_[4] - b_[4]) <= 1e-12 * a_[4]
+    # a pool kept for several sweeps; "auto" = as many budgets side by side as their eigen-solve launches fit on the GPU
+    with farm.SweepPool(fixed, cand, n, streams="auto") as pool:
+        ctas, sms = pool.macs[0]._h.lanczos_footprint()
+        assert 1 <= ctas <= sms and pool.streams == max(1, min(sms // ctas, 8))
+        for _ in range(2):
+            resp = pool.sweep(budgets, lambda k: synth.first_k_init(9000, k), max_iters=5, comm=None)
+            for a_, b_ in zip(res, resp):
+                assert a_[0] == b_[0] and np.array_equal(a_[1], b_[1]) and np.array_equal(a_[2], b_[2]) and a_[3] == b_[3]
 
 
 def test_farm_sweep_two_gpus_nccl():
