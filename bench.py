@@ -126,6 +126,15 @@ def cpu_fw(fixed, cand, n, k, x0, budget_s, max_steps):
     return done, time.perf_counter() - t0, fs
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs run on rank 0 alone and may use the whole host."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+
+
 def threads_used():
     try:
         from threadpoolctl import threadpool_info
@@ -137,6 +146,7 @@ def threads_used():
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    use_all_host_threads()
     fixed, cand, n, k, x0 = make_problem(0)
     if args.warmup > 0:
         cpu_fw(fixed, cand, n, k, x0, 0.0, 1)  # one untimed iteration: imports, page-in
