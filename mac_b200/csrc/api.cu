@@ -1244,8 +1244,10 @@ void launch_topk(macb_ctx* c, const double* g, const double* x, int64_t k, uint8
         return;
     }
     const int grid = c->grid_for(m);
-    k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
-    c->c_launches++;
+    if (k <= 0) {   // nothing to find: "take none" state (for k > 0 the select kernels write every field of the state themselves)
+        k_sel_init<<<1, kBlock, 0, c->stream>>>(st, (long long)k);
+        c->c_launches++;
+    }
     if (k > 0 && m <= kSel2SmallMax) {
         k_sel2_small<<<1, kSel2Block, kSel2Bins * sizeof(unsigned int), c->stream>>>(m, g, (long long)k, st);
         c->c_launches += 1;
