@@ -1682,7 +1682,11 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
             const double slope = (log(est) - log(est_prev)) / (double)(k - k_prev);
             const double pred = (log(target) - log(est)) / slope;
             const double cap = fmax(16.0, 0.25 * (double)k);
-            nk = need + (int)fmax(4.0, fmin(0.5 * pred, cap));
+            // never closer than a check takes (its cost grows with k: ~8 Lanczos steps at k = 190 at the headline size): checks
+            // spaced closer than that queue up behind each other, and the decision then lags the coefficients by the sum of
+            // their durations (measured: 15 steps) instead of one
+            const double min_gap = 4.0 * (double)max(1, (k + 48) / 96);
+            nk = need + (int)fmax(min_gap, fmin(0.5 * pred, cap));
         }
         if (theta_prev < inf) theta_delta = 2.0 * fabs(theta_prev - theta);
         theta_prev = theta;

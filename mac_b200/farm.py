@@ -124,6 +124,7 @@ class SweepPool:
         self.dev = local_rank if device is None else device
         self.fixed, self.cand, self.n, self.m = fixed, cand, n, len(cand[0])
         self.macs = [MAC(fixed, cand, n, device=self.dev)]
+        self._built = set()
         if streams == "auto":
             ctas, sms = self.macs[0]._h.lanczos_footprint()
             streams = max(1, min(sms // max(ctas, 1), 8))
@@ -136,6 +137,11 @@ class SweepPool:
             self.macs.append(None)
         if self.macs[slot] is None:
             self.macs[slot] = MAC(self.fixed, self.cand, self.n, device=self.dev)
+        if slot not in self._built:
+            # build the engine now (layout, basis: a multi-GB cudaMalloc synchronises the device), not inside some later sweep in
+            # which this worker happens to get its first budget
+            self.macs[slot]._h.lanczos_footprint()
+            self._built.add(slot)
         return self.macs[slot]
 
     def sweep(self, budgets, x_init_fn, max_iters=20, comm="env", **solve_kw):
@@ -184,6 +190,12 @@ class SweepPool:
         nthreads = min(self.streams, max(len(mine), 1))
         while len(self.macs) < nthreads:
             self.macs.append(None)
+        if any(slot not in self._built for slot in range(nthreads)):   # first use: all handles and engines exist before any budget is solved
+            builders = [threading.Thread(target=self._mac, args=(slot,)) for slot in range(nthreads)]
+            for t in builders:
+                t.start()
+            for t in builders:
+                t.join()
         threads = [threading.Thread(target=worker, args=(slot,)) for slot in range(nthreads)]
         for t in threads:
             t.start()

@@ -1,0 +1,3 @@
+python tools/scratch/rrstat2.py 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 --no-hbm-spmv 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); c=d['config']; print(d['value'], d['ms_per_step'], d['e2e']['value'], c['lanczos_us_per_step'], c['lanczos_steps_per_solve'], {k:v['seconds'] for k,v in c['ksweep'].items() if isinstance(v,dict)})"
