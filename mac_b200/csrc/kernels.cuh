@@ -1459,9 +1459,9 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
         RR_STAGE(0);
         // ---- bounds: Gershgorin, smallest diagonal entry, largest squared off-diagonal -- running values, only the rows that
         // are new (or whose lower neighbour is) are looked at; a row's older, smaller radius stays in the min / max harmlessly
-        {
+        if (tid < 32) {   // a handful of new rows per check: one warp
             double v0 = inf, v1 = -inf, v2 = inf, v3 = 0.0;
-            for (int i = max(k_bounds - 1, 0) + tid; i < k; i += nt) {
+            for (int i = max(k_bounds - 1, 0) + tid; i < k; i += 32) {
                 // (shared copies while they reach: a dependent global load costs ~2 500 cycles under the solver's traffic)
                 const bool sm_ok = i + 1 < cap_s;
                 const double ai = sm_ok ? a_s[i] : ld_relaxed_f64(R.a + i);
@@ -1479,16 +1479,13 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
                 v2 = fmin(v2, __shfl_xor_sync(0xffffffffu, v2, o));
                 v3 = fmax(v3, __shfl_xor_sync(0xffffffffu, v3, o));
             }
-            __syncthreads();
-            if ((tid & 31) == 0) {
-                red4[tid >> 5] = v0; red4[32 + (tid >> 5)] = v1; red4[64 + (tid >> 5)] = v2; red4[96 + (tid >> 5)] = v3;
+            if (tid == 0) {
+                red4[0] = v0; red4[1] = v1; red4[2] = v2; red4[3] = v3;
             }
-            __syncthreads();
-            for (int w = 0; w < (nt >> 5); ++w) {
-                gl = fmin(gl, red4[w]); gu = fmax(gu, red4[32 + w]); amin = fmin(amin, red4[64 + w]); bmax = fmax(bmax, red4[96 + w]);
-            }
-            k_bounds = k;
         }
+        __syncthreads();
+        gl = fmin(gl, red4[0]); gu = fmax(gu, red4[1]); amin = fmin(amin, red4[2]); bmax = fmax(bmax, red4[3]);
+        k_bounds = k;
         const double pivmin = fmax(dmin, dmin * bmax) * 4.0;
         const double tnorm = fmax(fabs(gl), fabs(gu));
         const bool in_s = k + 9 <= cap_s;
@@ -1596,61 +1593,83 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
             else if (tid == 32) rr_three_term_up(pa, pb, pbinv, k, theta, pdm);
         }
         __syncthreads();
-        {   // r = argmax |f_i| (ties -> smallest index)
+        // The rest of the pass -- joining the two recurrences at r = argmax |f_i| (ties -> smallest index), normalisation, the
+        // estimate, the Rayleigh quotient -- is a few hundred entries: ONE warp with shuffle reductions.  (Spread over the 1 024
+        // threads with block-wide reductions it cost 9 400 cycles per pass, more than the two recurrences: measured.)
+        if (tid < 32) {
             double best = -1.0;
             int bi = 0;
-            for (int i = tid; i < k; i += nt) {
+            for (int i = tid; i < k; i += 32) {
                 const double v = fabs(pdp[i]);
                 if (v > best) {
                     best = v;
                     bi = i;
                 }
             }
-            const double bmaxv = rr_block_max(best, red);
-            if (tid == 0) s_kr = 1 << 30;
-            __syncthreads();
-            if (best == bmaxv) atomicMin(&s_kr, bi);
-            __syncthreads();
-        }
-        const int r_tw = s_kr;
-        const double fr = pdp[r_tw], gr = pdm[r_tw];
-        bool vec_ok = fabs(fr) > 0.0 && fabs(fr) < inf && fabs(gr) > 0.0 && fabs(gr) < inf;
-        const double gscale = vec_ok ? fr / gr : 0.0;
-        double ssq = 0.0;
-        for (int i = tid; i < k; i += nt) {
-            const double v = (i <= r_tw) ? pdp[i] : gscale * pdm[i];
-            ps[i] = v;
-            ssq = fma(v, v, ssq);
-        }
-        ssq = rr_block_sum(ssq, red);
-        vec_ok = vec_ok && ssq > 0.0 && ssq < inf;
-        const double inv = vec_ok ? 1.0 / sqrt(ssq) : 0.0;
-        const double s_last = vec_ok ? ((k - 1 <= r_tw) ? pdp[k - 1] : gscale * pdm[k - 1]) : 0.0;
-        RR_STAGE(4);
-        est = vec_ok ? fabs(pb[k]) * fabs(s_last) * inv : inf;
-        exhausted = invariant || need >= R.k_limit;
-        s_inv = inv;
-        s_vok = vec_ok;
-        if (!vec_ok || polish == 1 || k == 1) break;
-        // theta is known to ~1e-7 only (multisection stops there, a frozen theta is the previous check's).  The vector just
-        // computed is one step of inverse iteration with that shift, so its Rayleigh quotient is accurate to
-        // d(theta) (d(theta) / gap)^2 -- Rayleigh-quotient iteration converges cubically -- and the SECOND pass, with the
-        // polished theta, gives the tail of the eigenvector that the estimate needs: an error d(theta) in the shift
-        // contaminates the vector with other Ritz vectors (last entries ~0.1) at the level d(theta) / gap, far above the
-        // 1e-10 the tail of a converged pair has (measured: with theta to 1e-7 and no polish the estimate stalls at 5e-4).
-        {
-            double num = 0.0;
-            for (int i = tid; i < k; i += nt) {
-                double t = pa[i] * ps[i];
-                if (i > 0) t = fma(pb[i], ps[i - 1], t);
-                if (i + 1 < k) t = fma(pb[i + 1], ps[i + 1], t);
-                num = fma(ps[i], t, num);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) {
+                    best = ob;
+                    bi = oi;
+                }
             }
-            num = rr_block_sum(num, red);
-            const double theta_rq = num * inv * inv;
-            if (precise && !(fabs(theta_rq - theta0) <= 1e-9 * fmax(fabs(theta0), 1e-300))) break;   // keep the bisected pair
-            theta = theta_rq;
+            const int r_tw = bi;
+            const double fr = pdp[r_tw], gr = pdm[r_tw];
+            bool vec_ok = fabs(fr) > 0.0 && fabs(fr) < inf && fabs(gr) > 0.0 && fabs(gr) < inf;
+            const double gscale = vec_ok ? fr / gr : 0.0;
+            double ssq = 0.0;
+            for (int i = tid; i < k; i += 32) {
+                const double v = (i <= r_tw) ? pdp[i] : gscale * pdm[i];
+                ps[i] = v;
+                ssq = fma(v, v, ssq);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            vec_ok = vec_ok && ssq > 0.0 && ssq < inf;
+            const double inv = vec_ok ? 1.0 / sqrt(ssq) : 0.0;
+            const double s_last = vec_ok ? ((k - 1 <= r_tw) ? pdp[k - 1] : gscale * pdm[k - 1]) : 0.0;
+            double theta_new = theta;
+            int leave = (!vec_ok || polish == 1 || k == 1) ? 1 : 0;
+            if (!leave) {
+                // theta is known to ~1e-7 only (multisection stops there, a frozen theta is the previous check's).  The vector just
+                // computed is one step of inverse iteration with that shift, so its Rayleigh quotient is accurate to
+                // d(theta) (d(theta) / gap)^2 -- Rayleigh-quotient iteration converges cubically -- and the SECOND pass, with the
+                // polished theta, gives the tail of the eigenvector that the estimate needs: an error d(theta) in the shift
+                // contaminates the vector with other Ritz vectors (last entries ~0.1) at the level d(theta) / gap, far above the
+                // 1e-10 the tail of a converged pair has (measured: with theta to 1e-7 and no polish the estimate stalls at 5e-4).
+                __syncwarp();
+                double num = 0.0;
+                for (int i = tid; i < k; i += 32) {
+                    double t = pa[i] * ps[i];
+                    if (i > 0) t = fma(pb[i], ps[i - 1], t);
+                    if (i + 1 < k) t = fma(pb[i + 1], ps[i + 1], t);
+                    num = fma(ps[i], t, num);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) num += __shfl_xor_sync(0xffffffffu, num, o);
+                const double theta_rq = num * inv * inv;
+                if (precise && !(fabs(theta_rq - theta0) <= 1e-9 * fmax(fabs(theta0), 1e-300))) leave = 1;   // keep the bisected pair
+                else theta_new = theta_rq;
+            }
+            if (tid == 0) {
+                red[0] = vec_ok ? fabs(pb[k]) * fabs(s_last) * inv : inf;
+                red[1] = inv;
+                red[2] = theta_new;
+                s_kr = (vec_ok ? 1 : 0) | (leave ? 2 : 0);
+            }
         }
+        __syncthreads();
+        RR_STAGE(4);
+        est = red[0];
+        s_inv = red[1];
+        theta = red[2];
+        s_vok = (s_kr & 1) != 0;
+        exhausted = invariant || need >= R.k_limit;
+        const bool leave_polish = (s_kr & 2) != 0;
+        __syncthreads();   // red / s_kr are reused by the next pass
+        if (leave_polish) break;
         }   // polish
         {   // is the cheap attempt credible?
             const bool moved = !(fabs(theta - theta0) <= 1e-5 * fmax(fabs(theta0), 1e-300));
@@ -1682,7 +1701,7 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
             const double slope = (log(est) - log(est_prev)) / (double)(k - k_prev);
             const double pred = (log(target) - log(est)) / slope;
             const double cap = fmax(16.0, 0.25 * (double)k);
-            // never closer than a check takes (its cost grows with k: ~8 Lanczos steps at k = 190 at the headline size): checks
+            // never closer than a check takes (its cost grows with k: 4-6 Lanczos steps at k = 190 at the headline size): checks
             // spaced closer than that queue up behind each other, and the decision then lags the coefficients by the sum of
             // their durations (measured: 15 steps) instead of one
             const double min_gap = 4.0 * (double)max(1, (k + 48) / 96);
