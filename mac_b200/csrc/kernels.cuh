@@ -1223,7 +1223,8 @@ __device__ __forceinline__ void rr_three_term_down_smem(unsigned int a_sh, unsig
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (i + j + 1 < k) {
-                const double fn = -fma(ac[j] - theta, f1, bc[j] * f0) * vc[j];
+                // one fused multiply-add on the dependency chain: the two products below do not depend on f1
+                const double fn = fma((theta - ac[j]) * vc[j], f1, -(bc[j] * vc[j]) * f0);
                 rr_sts(f_sh + 8u * (unsigned int)(i + j + 1), fn);
                 f0 = f1;
                 f1 = fn;
@@ -1258,7 +1259,7 @@ __device__ __forceinline__ bool rr_three_term_up_smem(unsigned int a_sh, unsigne
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (i - j >= 1) {
-                const double gn = -fma(ac[j] - theta, g1, bc[j] * g0) * vc[j];   // g_{i-j-1}
+                const double gn = fma((theta - ac[j]) * vc[j], g1, -(bc[j] * vc[j]) * g0);   // g_{i-j-1}
                 rr_sts(g_sh + 8u * (unsigned int)(i - j - 1), gn);
                 g0 = g1;
                 g1 = gn;
