@@ -1695,8 +1695,9 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
         }
         }
         RR_STAGE(5);
-        // ---- next check point: a function of the coefficients only (same rule as the host used: half-way to the step at
-        // which the geometric decay of the estimate is predicted to cross the target, never closer than 4 steps)
+        // ---- next check point: a function of the coefficients only, so that a solve is a pure function of its input: from the
+        // geometric decay of the estimate, half-way to the step at which it is predicted to cross the target -- the predicted
+        // step itself once that is near -- and never closer than a check takes
         int nk = rr_next_check(need, R.check_div);
         if (est_prev > 0.0 && est > target && est < est_prev && k > k_prev) {
             const double slope = (log(est) - log(est_prev)) / (double)(k - k_prev);
@@ -1706,7 +1707,9 @@ __device__ __noinline__ void lz_rr_main(const RrArgs& R, double* smem, int smem_
             // spaced closer than that queue up behind each other, and the decision then lags the coefficients by the sum of
             // their durations (measured: 15 steps) instead of one
             const double min_gap = 4.0 * (double)max(1, (k + 48) / 96);
-            nk = need + (int)fmax(min_gap, fmin(0.5 * pred, cap));
+            // close to the crossing (within three gaps): go for the predicted step itself; further away: half-way, the decay
+            // rate is not settled yet
+            nk = need + (int)fmax(min_gap, (pred <= 3.0 * min_gap) ? ceil(pred) + 1.0 : fmin(0.5 * pred, cap));
         }
         if (theta_prev < inf) theta_delta = 2.0 * fabs(theta_prev - theta);
         theta_prev = theta;
