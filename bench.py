@@ -1,7 +1,7 @@
 """Headline benchmark: Frank-Wolfe iterations/sec (= Fiedler solves/sec) on BASELINE.json configs[4]
 (chain + random graph, n = 100 000, 1 000 000 candidate edges, K = 200 000), one graph per GPU.
 
-    python bench.py --gpus 1 --steps 50 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
 
@@ -407,7 +407,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)   # max_iters of the reference's g2o protocol (g2o_experiment.py:319)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
