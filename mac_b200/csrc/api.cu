@@ -485,7 +485,7 @@ void launch_persist(macb_ctx* c, int nphases, bool async = false) {
         CK(cudaLaunchCooperativeKernel((void*)k_lanczos_small2, dim3(R.enabled ? 2 : 1), dim3(kPBlock), sparams, c->slots_smem, c->stream));
     } else if (c->persist_v == 5) {
         LzJdsArgs J{c->d_row_start, c->d_jcol, c->d_jval, c->d_jd, c->pipe_pos_cap, c->pipe_slot_cap, c->d_xrec, c->d_diag, c->d_jrow};
-        LzPipeArgs P{c->d_sc, c->d_zprev, nullptr, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
+        LzPipeArgs P{c->d_sc, c->d_zprev, c->rr_launch.enabled ? c->d_dev_stop : nullptr};
         RrArgs R = c->rr_launch;
         R.smem_doubles = (int)(c->pipe_smem / 8);
         if (R.enabled) {   // device-side decision: nothing is streamed to, or polled from, the host

@@ -867,19 +867,10 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_slots(LzPersistArgs a, L
     }
 }
 
-// ---- K3, slot-parallel form with jagged-diagonal staging (default when every CTA's range is one chunk) ----------
-// Same state, recurrence, records and outputs as k_lanczos_slots.  Three differences, all aimed at the cycles of a
-// step that are NOT gathers (clock64 stamps on B200 at the headline size: gathers 16.8 k cycles = the L1TEX
-// divergent-gather floor, row sums + block reduce 6.0 k, barrier + record fetch 4.3-5.3 k, coefficient chain 0.9 k):
-//  * the slots of a CTA are stored in jagged-diagonal order (rows sorted by decreasing length, diagonal d = the
-//    d-th slot of every row that has one): pass 1 is unchanged (thread j <-> slot j, coalesced), and in pass 2
-//    thread t sums prod[jd[d] + t] -- consecutive threads read consecutive words, so the row sums are free of the
-//    ~4-way bank conflicts a CSR-ordered product buffer gives, and warps are uniform in trip count;
-//  * everything that is constant over the launch (row id, length, slot range, diagonal starts, column indices)
-//    lives in registers / shared memory: no global load sits between the barrier and the first gather;
-//  * the first batch of gathers of step j+1 is issued straight after the barrier of step j, BEFORE the CTA fetches
-//    the 148 partial-sum records and runs the (long-latency, double-precision) coefficient chain: the gathers need
-//    only addresses, the coefficients are needed when the products are formed.
+// ---- layout of the pipelined Lanczos kernel (k_lanczos_pipe, below): host side in build_slice_layout (api.cu) ----------
+// History of the product buffer, all measured on B200 at the headline size: CSR order (4-way bank conflicts in the row sums)
+// -> jagged diagonals (round 1: consecutive threads read consecutive words, uniform trip counts, but a table of diagonal
+// starts between the loads) -> 32-row slices with an odd lane stride (this round: addresses known up front, no predication).
 constexpr int kLzSlice = 33;      // lane stride of a slice (doubles): odd, so that the entry index moves the shared-memory bank
 constexpr int kLzSliceTab = 64;   // ints per CTA in the slice table: (base, length) of up to 32 slices
 struct LzJdsArgs {
@@ -924,7 +915,7 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
     return k;   // lane l holds the total of value 2 * (l >> 4) + ((l >> 3) & 1)
 }
 
-// ---- K3, pipelined jagged-diagonal form (default): the reduction leaves the critical path ---------------------------------------
+// ---- K3, pipelined form (default): the reduction leaves the critical path ---------------------------------------
 // Its predecessor (round 1's k_lanczos_vec: same layout, plain Lanczos) spent a quarter of every step in the grid-wide exchange of the four partial sums (three dependent L2 round
 // trips) plus the wait for the slowest CTA, because the coefficients alpha_j, beta_j of step j depend on z_j = L u_j, the
 // result of that very step's SpMV.  Here the recurrence is rearranged (Ghysels/Vanroose-style pipelining) so that the SpMV
@@ -1060,7 +1051,6 @@ struct RrArgs {
 struct LzPipeArgs {
     const LzScalars* sc;   // sc->shift = trace(L)/n (k_assemble)
     double* zprev;         // [n] z_{j-1} of the CTA's rows across launches (engine numbering)
-    double* unused;
     int* dev_stop;         // device-resident stop flag raised by the Rayleigh-Ritz CTA (may be nullptr)
 };
 
