@@ -111,6 +111,33 @@ def farm_comm(device=None):
     return _COMM
 
 
+def pack_sweep_records(local, owner, rank, nranks, m):
+    """This rank's results as one fixed-size array for `macb_comm_allgather`: a row per budget the rank owns (in budget order),
+    [rounded mask (m), relaxed solution (m), dual bound, lambda2]; every rank sends max-over-ranks rows (zero padded)."""
+    import numpy as np
+    per_rank = [[i for i in range(len(owner)) if owner[i] == r] for r in range(nranks)]
+    slots = max(1, max(len(p) for p in per_rank))
+    buf = np.zeros((slots, 2 * m + 2))
+    for j, i in enumerate(per_rank[rank]):
+        k, rounded, w, u, lam = local[i]
+        buf[j, :m] = rounded
+        buf[j, m:2 * m] = w
+        buf[j, 2 * m] = u
+        buf[j, 2 * m + 1] = lam
+    return buf
+
+
+def unpack_sweep_records(allb, owner, budgets, m):
+    """Inverse of `pack_sweep_records` over the gathered array [nranks, rows, 2 m + 2]: results in budget order."""
+    nranks = allb.shape[0]
+    out = [None] * len(budgets)
+    for r in range(nranks):
+        for j, i in enumerate([i for i in range(len(budgets)) if owner[i] == r]):
+            rec = allb[r, j]
+            out[i] = (budgets[i], rec[:m].astype("u1"), rec[m:2 * m].copy(), float(rec[2 * m]), float(rec[2 * m + 1]))
+    return out
+
+
 class SweepPool:
     """The graph of one budget sweep resident on this rank's GPU, `streams` times: one MAC handle (own CUDA stream, own host
     thread while a sweep runs) per budget solved concurrently.  A pose graph (n <= 1e4) occupies 6-21 of the 148 SMs, so
@@ -205,23 +232,7 @@ class SweepPool:
             raise errors[0]
         if comm is None:
             return [local[i] for i in range(len(budgets))]
-        # one fixed-size record per budget: rounded mask, relaxed solution, dual bound, lambda2; every rank sends the same count
-        per_rank = [[i for i in range(len(budgets)) if owner[i] == r] for r in range(nranks)]
-        slots = max(1, max(len(p) for p in per_rank))
-        buf = np.zeros((slots, 2 * m + 2))
-        for j, i in enumerate(mine):
-            k, rounded, w, u, lam = local[i]
-            buf[j, :m] = rounded
-            buf[j, m:2 * m] = w
-            buf[j, 2 * m] = u
-            buf[j, 2 * m + 1] = lam
-        allb = comm.allgather(buf)
-        out = [None] * len(budgets)
-        for r in range(nranks):
-            for j, i in enumerate(per_rank[r]):
-                rec = allb[r, j]
-                out[i] = (budgets[i], rec[:m].astype("u1"), rec[m:2 * m].copy(), float(rec[2 * m]), float(rec[2 * m + 1]))
-        return out
+        return unpack_sweep_records(comm.allgather(pack_sweep_records(local, owner, myrank, nranks, m)), owner, budgets, m)
 
     def close(self):
         for mac in self.macs:

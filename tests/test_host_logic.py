@@ -311,3 +311,24 @@ def test_unique_id_exchange_over_tcp():
     for t in ts:
         t.join(timeout=60)
     assert got == {0: uid, 1: uid, 2: uid}
+
+
+def test_sweep_records_round_trip_through_a_fake_allgather():
+    """farm.SweepPool with several ranks: every rank packs the budgets `macb_sweep_owner` gave it, one allgather, every rank unpacks
+    the same list in budget order (the GPU test of this path needs two GPUs)."""
+    from mac_b200 import _lib, farm
+    rng = np.random.default_rng(5)
+    m = 37
+    budgets = [3, 30, 11, 36, 7, 18, 25]
+    for nranks in (1, 2, 3, 8):
+        owner = _lib.sweep_owner(budgets, m, nranks)
+        truth = {i: (k, (rng.random(m) < 0.5).astype("u1"), rng.random(m), float(rng.random()), float(rng.random())) for i, k in enumerate(budgets)}
+        bufs = []
+        for r in range(nranks):
+            local = {i: truth[i] for i in range(len(budgets)) if owner[i] == r}
+            bufs.append(farm.pack_sweep_records(local, owner, r, nranks, m))
+        assert len({b.shape for b in bufs}) == 1                      # equal counts on every rank, as ncclAllGather needs
+        out = farm.unpack_sweep_records(np.stack(bufs), owner, budgets, m)
+        for i, (k, r_, w, u, lam) in enumerate(out):
+            assert k == budgets[i] and np.array_equal(r_, truth[i][1]) and np.array_equal(w, truth[i][2])
+            assert u == truth[i][3] and lam == truth[i][4]
