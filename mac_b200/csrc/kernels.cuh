@@ -1906,13 +1906,20 @@ __global__ void __launch_bounds__(kPBlock, 1) k_lanczos_pipe(LzPersistArgs a, Lz
             if (pb >= ncta) y0 = 0.0;
             y2 = fabs(y2);
             const double t = warp_sum4(y0, y1, y2, y3, lane);
-            if ((lane & 7) == 0) sh.pollsum[(lane >> 3) * 8 + (warp - first_poll_warp)] = t;
-            asm volatile("bar.sync 1, %0;" ::"r"(poll_warps * 32) : "memory");
+            double P1, P2, P3, P4;
+            if (poll_warps == 1) {   // up to 32 CTAs (pose graphs): one polling warp, the totals are already in its lanes
+                P1 = __shfl_sync(0xffffffffu, t, 0); P2 = __shfl_sync(0xffffffffu, t, 8);
+                P3 = __shfl_sync(0xffffffffu, t, 16); P4 = __shfl_sync(0xffffffffu, t, 24);
+            } else {
+                if ((lane & 7) == 0) sh.pollsum[(lane >> 3) * 8 + (warp - first_poll_warp)] = t;
+                asm volatile("bar.sync 1, %0;" ::"r"(poll_warps * 32) : "memory");
+                P1 = P2 = P3 = P4 = 0.0;
+                if (tid == kPBlock - 32)
+                    for (int w = 0; w < poll_warps; ++w) {   // fixed order: identical totals on every CTA
+                        P1 += sh.pollsum[w]; P2 += sh.pollsum[8 + w]; P3 += sh.pollsum[16 + w]; P4 += sh.pollsum[24 + w];
+                    }
+            }
             if (tid == kPBlock - 32) {
-                double P1 = 0.0, P2 = 0.0, P3 = 0.0, P4 = 0.0;
-                for (int w = 0; w < poll_warps; ++w) {   // fixed order: identical totals on every CTA
-                    P1 += sh.pollsum[w]; P2 += sh.pollsum[8 + w]; P3 += sh.pollsum[16 + w]; P4 += sh.pollsum[24 + w];
-                }
                 const LzCoef c0 = lz_coefficients(P1, P2, P3, P4, (phase > 0) ? sh.beta_prev : 0.0, sh.usum_prev, sh.inv_n);
                 sh.coef[0] = c0.k1; sh.coef[1] = c0.k2; sh.coef[2] = c0.k3; sh.coef[3] = c0.k4;
                 sh.coef[4] = c0.alpha; sh.coef[5] = c0.beta;
