@@ -146,6 +146,29 @@ def test_fiedler_small_and_awkward_graphs():
         h.close()
 
 
+def test_hub_graph_falls_back_to_the_chunked_engine():
+    """A node of degree 3000 makes the first 32-row slice of its CTA 3000 entries long: more product positions than the pipelined
+    kernel's 15-bit position field.  The handle must pick the chunked engine by itself and still match a dense eigen-solve."""
+    rng = np.random.default_rng(21)
+    n = 6000
+    ei = np.r_[np.arange(n - 1), np.zeros(3000, dtype=np.int64)]
+    ej = np.r_[np.arange(1, n), rng.choice(np.arange(2, n), size=3000, replace=False)]
+    w = rng.uniform(0.5, 2.0, len(ei))
+    ci = rng.integers(0, n, 8000); cj = rng.integers(0, n, 8000)
+    keep = np.abs(ci - cj) > 1
+    ci, cj = ci[keep], cj[keep]
+    ck = rng.uniform(0.5, 2.0, len(ci))
+    mac = MAC((ei, ej, w), (ci, cj, ck), n)
+    x = (rng.random(len(ci)) < 0.5).astype(float)
+    lam, v = mac.fiedler_pair(x)
+    assert mac._h.lanczos_kernel_name() != "k_lanczos_pipe" and mac.last_info["converged"]
+    L = orc.OracleMAC((ei, ej, w), (ci, cj, ck), n).laplacian(x)
+    ev = np.linalg.eigvalsh(L.toarray())
+    assert abs(lam - ev[1]) <= 1e-8 * ev[1]
+    assert orc.residual_l1(L, lam, v) < 1e-8
+    mac.close()
+
+
 def test_disconnected_graph_has_zero_connectivity():
     # the reference skips this case (tests/utils/test_fiedler.py:43-50); the device solver returns ~0
     ei = np.array([0, 0, 1, 3, 3, 4])
