@@ -118,8 +118,8 @@ struct macb_ctx {
     bool sj_col16 = false;
     int64_t* d_sj_chunk_slot = nullptr;
     double* d_sj_val = nullptr;
-    int vec_batch = 5;             // gathers in flight per thread in k_lanczos_vec (3..8, chosen from the slots per thread)
-    bool pipe = true;              // k_lanczos_pipe (pipelined recurrence, reduction off the critical path) instead of k_lanczos_vec
+    int vec_batch = 5;             // gathers in flight per thread in k_lanczos_pipe (3..8, chosen from the slots per thread)
+    bool pipe = true;              // k_lanczos_pipe is built (pipelined recurrence, reduction off the critical path)
     size_t pipe_smem = 0;
     // Two sets of read-back buffers / events, so that iteration i+1 of the Frank-Wolfe loop can be enqueued before the host has
     // looked at the scalars of iteration i (set 0 = the members above; use_slot() points the members at a set)
@@ -155,10 +155,10 @@ struct macb_ctx {
     long long* d_ptiming = nullptr;
     std::vector<int32_t> h_rp;  // host copy of row_ptr (row partition)
     std::vector<int32_t> h_col, h_eid;  // host copies of the pattern until the persistent engine has been set up
-    // jagged-diagonal staging of the slot-parallel kernel (k_lanczos_jds, persist_v == 5)
+    // sliced layout of the pipelined kernel (k_lanczos_pipe, persist_v == 5)
     int *d_jrow = nullptr, *d_jlen = nullptr, *d_jcol = nullptr, *d_jeid = nullptr, *d_jd = nullptr;
     double* d_jval = nullptr;
-    double* d_xrec = nullptr;      // all-to-all barrier inboxes of k_lanczos_jds
+    double* d_xrec = nullptr;      // inboxes of the all-to-all record exchange of k_lanczos_pipe
     int pipe_pos_cap = 0, pipe_slot_cap = 0;   // k_lanczos_pipe: product positions / slots per CTA (shared-memory sizes)
 
     // reductions / selection
@@ -2149,8 +2149,8 @@ int macb_lanczos_kernel_time(macb_handle h, double* ms, int64_t* phases, double*
     if (ms) *ms = h->lz_kernel_ms;
     if (phases) *phases = h->lz_kernel_phases;
     // one Lanczos phase = one SpMV ((nnz + n) * 12 + 4 (n + 1) + 16 n) plus what the engine writes per node:
-    // the 32-byte state sector and the 8-byte basis entry (sector engines), or the new vector entry, the basis entry
-    // and the poison word (k_lanczos_vec)
+    // the 32-byte state sector and the 8-byte basis entry (sector engines), or the new z and u entries and the basis entry
+    // (k_lanczos_pipe)
     if (algo_bytes_per_phase && h->lz_algo_bytes > 0.0 && h->lz_kernel_phases > 0) {
         // device-side decision: bytes follow the ACTIVE slots of every timed launch (zero-weight slots issue no gather and no
         // weight load): sum over launches of phases x [(nnz_active + n) 12 + 4 (n + 1) + 16 n + 24 n] / phases
